@@ -1,0 +1,639 @@
+// ActorCritic forward / PPO loss / hand-written backward, fp32 CUDA-core path (K5-K8 anchor).
+//
+// Layer-wise: every nn.Linear (+ELU/Tanh) of `rsl_rl/modules/actor_critic.py` is one launch of
+// the tile GEMM in gemm_simt.cuh with the bias/activation (forward) or activation derivative
+// (backward) fused into its epilogue; the mini-batch gather (RS:189-201) is fused into the
+// first-layer operand loads (no gathered batch is materialised); the Conv1d history encoder
+// (AC:39-84) is expressed as three more GEMMs over re-packed weights.  The PPO loss
+// (PPO:199-221) and its derivative w.r.t. the network outputs is one elementwise kernel.
+#include <math.h>
+
+#include "gemm_simt.cuh"
+
+namespace dwbc {
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct Bump {
+  char* base;
+  int64_t off;
+  float* f(int64_t n) {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += align_up(n * (int64_t)sizeof(float), 256);
+    return p;
+  }
+};
+
+static inline int last(const int32_t* d, int n) { return d[n - 1]; }
+
+// ---- workspace plan ----------------------------------------------------------------------------
+struct Plan {
+  // forward activations (saved for backward)
+  float* priv[DWBC_MAX_LAYERS];   // priv encoder outputs; the last one is the latent z
+  float* ab[DWBC_MAX_LAYERS];     // actor backbone
+  float* al[DWBC_MAX_LAYERS];     // actor leg head hidden
+  float* aa[DWBC_MAX_LAYERS];     // actor arm head hidden
+  float* mean;                    // [rows, mean_ld] tanh outputs (leg | arm)
+  float* cb[DWBC_MAX_LAYERS];
+  float* cl[DWBC_MAX_LAYERS];
+  float* ca[DWBC_MAX_LAYERS];
+  float* value;                   // [rows, 2]
+  // history encoder
+  float* hproj;                   // [rows*T, 32]
+  float* hc1;                     // [rows*4, 20]
+  float* hc2;                     // [rows*3, 12]
+  float* zh;                      // [rows, latent]
+  float* hw1; float* hw2; float* hwl;      // re-packed weights
+  // gradients
+  float* g_leg; float* g_arm; float* g_vl; float* g_va; float* g_z;
+  float* d0; float* d1; float* d2;         // ping-pong [rows, maxw]
+  float* dz;                               // [rows, latent]
+  float* dzh;                              // [rows, latent] (dagger)
+  float* dh_a1; float* dh_a2;              // im2col-space grads of the conv inputs (dagger)
+  float* dh_c1; float* dh_proj;
+  float* dhw1; float* dhw2; float* dhwl;   // grads of the re-packed weights (dagger)
+  int mean_ld, maxw, latent;
+  int64_t bytes;
+};
+
+static int maxdim(const DwbcNetCfg& n) {
+  int m = 32;
+  auto up = [&](const int32_t* d, int k) { for (int i = 0; i < k; ++i) m = d[i] > m ? d[i] : m; };
+  up(n.priv_dims, n.n_priv_layers); up(n.actor_dims, n.n_actor_layers); up(n.critic_dims, n.n_critic_layers);
+  up(n.leg_dims, n.n_leg_layers); up(n.arm_dims, n.n_arm_layers);
+  return (int)align_up(m, 4);
+}
+
+static Plan make_plan(const DwbcNetCfg& n, int64_t rows, void* ws) {
+  Plan p{};
+  Bump b{reinterpret_cast<char*>(ws), 0};
+  p.latent = last(n.priv_dims, n.n_priv_layers);
+  p.maxw = maxdim(n);
+  p.mean_ld = (int)align_up(n.n_leg + n.n_arm, 4);
+  for (int i = 0; i < n.n_priv_layers; ++i) p.priv[i] = b.f(rows * align_up(n.priv_dims[i], 4));
+  for (int i = 0; i < n.n_actor_layers; ++i) p.ab[i] = b.f(rows * n.actor_dims[i]);
+  for (int i = 0; i < n.n_leg_layers; ++i) p.al[i] = b.f(rows * n.leg_dims[i]);
+  for (int i = 0; i < n.n_arm_layers; ++i) p.aa[i] = b.f(rows * n.arm_dims[i]);
+  p.mean = b.f(rows * p.mean_ld);
+  for (int i = 0; i < n.n_critic_layers; ++i) p.cb[i] = b.f(rows * n.critic_dims[i]);
+  for (int i = 0; i < n.n_leg_layers; ++i) p.cl[i] = b.f(rows * n.leg_dims[i]);
+  for (int i = 0; i < n.n_arm_layers; ++i) p.ca[i] = b.f(rows * n.arm_dims[i]);
+  p.value = b.f(rows * 2);
+  p.hproj = b.f(rows * n.num_hist * 32);
+  p.hc1 = b.f(rows * 4 * 20);
+  p.hc2 = b.f(rows * 3 * 12);
+  p.zh = b.f(rows * align_up(p.latent, 4));
+  p.hw1 = b.f(20 * 128); p.hw2 = b.f(10 * 40); p.hwl = b.f(32 * 36);
+  p.g_leg = b.f(rows * align_up(n.n_leg, 4)); p.g_arm = b.f(rows * align_up(n.n_arm, 4));
+  p.g_vl = b.f(rows); p.g_va = b.f(rows); p.g_z = b.f(rows * align_up(p.latent, 4));
+  p.d0 = b.f(rows * p.maxw); p.d1 = b.f(rows * p.maxw); p.d2 = b.f(rows * p.maxw);
+  p.dz = b.f(rows * align_up(p.latent, 4));
+  p.dzh = b.f(rows * align_up(p.latent, 4));
+  p.dh_a1 = b.f(rows * 4 * 128); p.dh_a2 = b.f(rows * 3 * 40);
+  p.dh_c1 = b.f(rows * 4 * 20); p.dh_proj = b.f(rows * n.num_hist * 32);
+  p.dhw1 = b.f(20 * 128); p.dhw2 = b.f(10 * 40); p.dhwl = b.f(32 * 36);
+  p.bytes = b.off;
+  return p;
+}
+
+static int check_net(const DwbcNetCfg* n) {
+  if (!n || n->abi_version != DWBC_ABI_VERSION) return DWBC_ERR_ARG;
+  if (n->n_priv_layers < 1 || n->n_priv_layers > DWBC_MAX_LAYERS || n->n_actor_layers < 1 || n->n_actor_layers > DWBC_MAX_LAYERS ||
+      n->n_critic_layers < 1 || n->n_critic_layers > DWBC_MAX_LAYERS || n->n_leg_layers < 1 || n->n_leg_layers > DWBC_MAX_LAYERS ||
+      n->n_arm_layers < 1 || n->n_arm_layers > DWBC_MAX_LAYERS)
+    return DWBC_ERR_UNSUPPORTED;
+  // history encoder: only the tsteps == 10 variant (AC:57-62) exists for widowGo1 (WGC:124)
+  if (n->num_hist != 10 || n->hist_proj != 30 || n->hist_c1 != 20 || n->hist_k1 != 4 || n->hist_s1 != 2 || n->hist_c2 != 10 ||
+      n->hist_k2 != 2 || n->hist_s2 != 1)
+    return DWBC_ERR_UNSUPPORTED;
+  if (last(n->priv_dims, n->n_priv_layers) > 32 || n->n_leg + n->n_arm > 32) return DWBC_ERR_UNSUPPORTED;
+  return DWBC_OK;
+}
+
+// ---- history-encoder weight re-packing ---------------------------------------------------------
+// conv1 [20,30,4] -> W1'[20][k*32+cin]; conv2 [10,20,2] -> W2'[10][k*20+cin]; linear [L,30] over the
+// channel-major flatten (c2*3+t) -> Wl'[L][t*12+c2].  Pad entries are zero.
+__global__ void hist_pack_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ wl,
+                                 float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ ol, int latent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 20 * 128) {
+    int c1 = i / 128, r = i % 128, k = r / 32, cin = r % 32;
+    o1[i] = cin < 30 ? w1[(c1 * 30 + cin) * 4 + k] : 0.0f;
+  }
+  if (i < 10 * 40) {
+    int c2 = i / 40, r = i % 40, k = r / 20, cin = r % 20;
+    o2[i] = w2[(c2 * 20 + cin) * 2 + k];
+  }
+  if (i < latent * 36) {
+    int j = i / 36, r = i % 36, t = r / 12, c2 = r % 12;
+    ol[i] = c2 < 10 ? wl[j * 30 + c2 * 3 + t] : 0.0f;
+  }
+}
+// inverse scatter of the re-packed weight gradients into the flat gradient (reference layouts)
+__global__ void hist_unpack_grad_kernel(const float* __restrict__ g1, const float* __restrict__ g2, const float* __restrict__ gl,
+                                        float* __restrict__ w1, float* __restrict__ w2, float* __restrict__ wl, int latent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 20 * 128) {
+    int c1 = i / 128, r = i % 128, k = r / 32, cin = r % 32;
+    if (cin < 30) w1[(c1 * 30 + cin) * 4 + k] = g1[i];
+  }
+  if (i < 10 * 40) {
+    int c2 = i / 40, r = i % 40, k = r / 20, cin = r % 20;
+    w2[(c2 * 20 + cin) * 2 + k] = g2[i];
+  }
+  if (i < latent * 36) {
+    int j = i / 36, r = i % 36, t = r / 12, c2 = r % 12;
+    if (c2 < 10) wl[j * 30 + c2 * 3 + t] = gl[i];
+  }
+}
+// col2im of the conv input gradients (overlapping windows) fused with the ELU derivative:
+// dst[m][t][c] = elu'(y[m][t][c]) * sum_{t'*stride + k == t} src[(m*To + t')][k*C + c]
+__global__ void col2im_dact_kernel(const float* __restrict__ src, const float* __restrict__ y, float* __restrict__ dst, int64_t rows,
+                                   int Tin, int C, int ldc, int To, int ksz, int stride) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = rows * Tin * ldc;
+  if (i >= total) return;
+  int c = (int)(i % ldc);
+  int t = (int)((i / ldc) % Tin);
+  int64_t m = i / ((int64_t)ldc * Tin);
+  float s = 0.0f;
+  if (c < C) {
+    for (int k = 0; k < ksz; ++k) {
+      int tt = t - k;
+      if (tt < 0 || tt % stride) continue;
+      int to = tt / stride;
+      if (to >= To) continue;
+      s += src[(m * To + to) * (int64_t)(ksz * ldc) + k * ldc + c];
+    }
+    float yy = y[i];
+    s *= (yy > 0.0f ? 1.0f : yy + 1.0f);
+  }
+  dst[i] = s;
+}
+
+__global__ void zero_cols_kernel(float* __restrict__ p, int64_t nrows, int ld, int c0) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = ld - c0;
+  if (i < nrows * w) p[(i / w) * ld + c0 + (i % w)] = 0.0f;
+}
+
+// ---- forward ------------------------------------------------------------------------------------
+#define TRY(x) do { int rc__ = (x); if (rc__ != DWBC_OK) return rc__; } while (0)
+
+static int hist_forward(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows,
+                        const Plan& p, cudaStream_t st) {
+  const int T = n.num_hist, L = p.latent, Lld = (int)align_up(L, 4);
+  hist_pack_kernel<<<(20 * 128 + 255) / 256, 256, 0, st>>>(P + n.off_hist_w[1], P + n.off_hist_w[2], P + n.off_hist_w[3], p.hw1, p.hw2,
+                                                           p.hwl, L);
+  // pad columns of the padded activation buffers are consumed by the next GEMM's K range
+  zero_cols_kernel<<<(unsigned)(((int64_t)rows * T * 2 + 255) / 256), 256, 0, st>>>(p.hproj, (int64_t)rows * T, 32, 30);
+  zero_cols_kernel<<<(unsigned)(((int64_t)rows * 3 * 2 + 255) / 256), 256, 0, st>>>(p.hc2, (int64_t)rows * 3, 12, 10);
+  RowMat hist = rowmat_grouped(obs + (n.num_obs - T * n.num_prop), idx, T, obs_stride, n.num_prop);
+  TRY(linear_fwd(hist, P + n.off_hist_w[0], n.num_prop, P + n.off_hist_b[0], p.hproj, 32, rows * T, 30, n.num_prop, ACT_ELU, 0, st));  // AC:80
+  RowMat a1 = rowmat_grouped(p.hproj, nullptr, 4, (int64_t)T * 32, 2 * 32);
+  TRY(linear_fwd(a1, p.hw1, 128, P + n.off_hist_b[1], p.hc1, 20, rows * 4, 20, 128, ACT_ELU, 0, st));                                  // AC:59
+  RowMat a2 = rowmat_grouped(p.hc1, nullptr, 3, 80, 20);
+  TRY(linear_fwd(a2, p.hw2, 40, P + n.off_hist_b[2], p.hc2, 12, rows * 3, 10, 40, ACT_ELU, 0, st));                                     // AC:60
+  TRY(linear_fwd(rowmat(p.hc2, 36), p.hwl, 36, P + n.off_hist_b[3], p.zh, Lld, rows, L, 36, ACT_ELU, 0, st));                           // AC:72
+  return DWBC_OK;
+}
+
+static int priv_forward(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows,
+                        const Plan& p, cudaStream_t st) {
+  RowMat h = rowmat_gather(obs + n.num_prop, idx, obs_stride);
+  int in = n.num_priv;
+  for (int l = 0; l < n.n_priv_layers; ++l) {
+    int out = n.priv_dims[l], ld = (int)align_up(out, 4);
+    TRY(linear_fwd(h, P + n.off_priv_w[l], in, P + n.off_priv_b[l], p.priv[l], ld, rows, out, in, ACT_ELU, 0, st));  // AC:219-221
+    h = rowmat(p.priv[l], ld);
+    in = out;
+  }
+  return DWBC_OK;
+}
+
+static int head_forward(const float* P, RowMat h, int in, int nl, const int32_t* dims, int n_out, const int64_t* ow, const int64_t* ob,
+                        float* const* acts, float* out, int64_t ldo, int last_act, int rows, cudaStream_t st) {
+  for (int l = 0; l < nl; ++l) {
+    TRY(linear_fwd(h, P + ow[l], in, P + ob[l], acts[l], dims[l], rows, dims[l], in, ACT_ELU, 0, st));
+    h = rowmat(acts[l], dims[l]);
+    in = dims[l];
+  }
+  return linear_fwd(h, P + ow[nl], in, P + ob[nl], out, ldo, rows, n_out, in, last_act, 0, st);
+}
+
+// Actor.forward (AC:204-217); latent z must already be in `z` (row stride zld)
+static int actor_forward(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows,
+                         const float* z, int zld, const Plan& p, cudaStream_t st) {
+  RowMat x = rowmat_gather(obs, idx, obs_stride);
+  const int in0 = n.num_prop + p.latent;
+  // backbone layer 0 over cat([obs_prop, z]) as two accumulating GEMMs (no concat buffer)
+  int single = n.n_actor_layers;
+  TRY(linear_fwd(x, P + n.off_actor_w[0], in0, P + n.off_actor_b[0], p.ab[0], n.actor_dims[0], rows, n.actor_dims[0], n.num_prop, ACT_NONE, 0, st));
+  TRY(linear_fwd(rowmat(z, zld), P + n.off_actor_w[0] + n.num_prop, in0, nullptr, p.ab[0], n.actor_dims[0], rows, n.actor_dims[0], p.latent,
+                 ACT_ELU, 1, st));
+  RowMat h = rowmat(p.ab[0], n.actor_dims[0]);
+  int in = n.actor_dims[0];
+  for (int l = 1; l < single; ++l) {
+    TRY(linear_fwd(h, P + n.off_actor_w[l], in, P + n.off_actor_b[l], p.ab[l], n.actor_dims[l], rows, n.actor_dims[l], in, ACT_ELU, 0, st));
+    h = rowmat(p.ab[l], n.actor_dims[l]);
+    in = n.actor_dims[l];
+  }
+  TRY(head_forward(P, h, in, n.n_leg_layers, n.leg_dims, n.n_leg, n.off_aleg_w, n.off_aleg_b, p.al, p.mean, p.mean_ld, ACT_TANH, rows, st));
+  TRY(head_forward(P, h, in, n.n_arm_layers, n.arm_dims, n.n_arm, n.off_aarm_w, n.off_aarm_b, p.aa, p.mean + n.n_leg, p.mean_ld, ACT_TANH, rows, st));
+  return DWBC_OK;
+}
+
+// Critic.forward (AC:280-286)
+static int critic_forward(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows,
+                          const Plan& p, float* value, cudaStream_t st) {
+  RowMat h = rowmat_gather(obs, idx, obs_stride);
+  int in = n.num_prop + n.num_priv;
+  for (int l = 0; l < n.n_critic_layers; ++l) {
+    TRY(linear_fwd(h, P + n.off_critic_w[l], in, P + n.off_critic_b[l], p.cb[l], n.critic_dims[l], rows, n.critic_dims[l], in, ACT_ELU, 0, st));
+    h = rowmat(p.cb[l], n.critic_dims[l]);
+    in = n.critic_dims[l];
+  }
+  TRY(head_forward(P, h, in, n.n_leg_layers, n.leg_dims, 1, n.off_cleg_w, n.off_cleg_b, p.cl, value, 2, ACT_NONE, rows, st));
+  TRY(head_forward(P, h, in, n.n_arm_layers, n.arm_dims, 1, n.off_carm_w, n.off_carm_b, p.ca, value + 1, 2, ACT_NONE, rows, st));
+  return DWBC_OK;
+}
+
+// ---- rollout sampling + log-prob (AC:326-345, PPO:119-123) -------------------------------------
+constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
+
+__global__ void act_finalize_kernel(const float* __restrict__ mean_in, int mean_ld, const float* __restrict__ std, const float* __restrict__ eps,
+                                    float* __restrict__ actions, float* __restrict__ log_prob, float* __restrict__ mean_out,
+                                    float* __restrict__ sigma_out, int rows, int n_leg, int n_act) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float lp[2] = {0.0f, 0.0f};
+  for (int i = 0; i < n_act; ++i) {
+    const float mu = mean_in[(int64_t)r * mean_ld + i], sg = std[i];
+    const float a = mu + sg * eps[(int64_t)r * n_act + i];
+    const float d = a - mu;
+    lp[i < n_leg ? 0 : 1] += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - LOG_SQRT_2PI;
+    actions[(int64_t)r * n_act + i] = a;
+    mean_out[(int64_t)r * n_act + i] = mu;
+    sigma_out[(int64_t)r * n_act + i] = sg;
+  }
+  log_prob[2 * r] = lp[0];
+  log_prob[2 * r + 1] = lp[1];
+}
+
+// ---- PPO loss and its derivative w.r.t. the network outputs (PPO:166-221) ----------------------
+struct LossArgs {
+  const float* mean; int mean_ld; const float* std; const float* value; const float* zp; int zld; const float* zh;
+  const float* actions; const float* old_logp; const float* old_values; const float* returns; const float* adv; const int64_t* idx;
+  float* g_leg; int gleg_ld; float* g_arm; int garm_ld; float* g_vl; float* g_va; float* g_z;
+  float* grad_std; float* losses;
+  int rows, n_leg, n_act, latent;
+  float clip, c_value, c_ent, c_reg, rho;
+  int clipped_value;
+};
+
+__global__ void __launch_bounds__(128) ppo_loss_kernel(const LossArgs a) {
+  __shared__ float red[4][4];
+  __shared__ float sred[32];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = r < a.rows;
+  const float inv2m = 1.0f / (2.0f * (float)a.rows), invm = 1.0f / (float)a.rows;
+  float l_surr = 0.0f, l_val = 0.0f, l_reg = 0.0f, l_ent = 0.0f;
+  float gstd[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) gstd[i] = 0.0f;
+  if (on) {
+    const int64_t src = a.idx ? a.idx[r] : r;
+    const float* mu = a.mean + (int64_t)r * a.mean_ld;
+    const float* act = a.actions + src * a.n_act;
+    float lp[2] = {0.0f, 0.0f}, ent[2] = {0.0f, 0.0f};
+    for (int i = 0; i < a.n_act; ++i) {
+      const float sg = a.std[i], d = act[i] - mu[i];
+      const int c = i < a.n_leg ? 0 : 1;
+      lp[c] += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - LOG_SQRT_2PI;          // AC:341-345
+      ent[c] += 0.5f + LOG_SQRT_2PI + logf(sg);                                  // AC:326-331 (0.5 log 2pi == log sqrt 2pi)
+    }
+    const float a0 = a.adv[2 * src], a1 = a.adv[2 * src + 1];
+    const float mix[2] = {a0 + a.rho * a1, a1 + a.rho * a0};                       // PPO:199-201
+    float glp[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float ratio = expf(lp[c] - a.old_logp[2 * src + c]);                   // PPO:202
+      const float rc = fminf(fmaxf(ratio, 1.0f - a.clip), 1.0f + a.clip);
+      const float s1 = -mix[c] * ratio, s2 = -mix[c] * rc;                         // PPO:203-205
+      l_surr += fmaxf(s1, s2);
+      const bool inside = ratio >= 1.0f - a.clip && ratio <= 1.0f + a.clip;
+      float g = 0.0f;                                                              // d max(s1,s2) / d ratio
+      if (s1 > s2) g = -mix[c];
+      else if (s1 == s2) g = 0.5f * -mix[c] + (inside ? 0.5f * -mix[c] : 0.0f);
+      else g = inside ? -mix[c] : 0.0f;
+      glp[c] = inv2m * g * ratio;
+      l_ent += ent[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < a.n_act) {
+        const float sg = a.std[i], d = act[i] - mu[i];
+        const int c = i < a.n_leg ? 0 : 1;
+        const float gmu = glp[c] * d / (sg * sg) * (1.0f - mu[i] * mu[i]);         // through tanh (AC:157,170)
+        if (c == 0) a.g_leg[(int64_t)r * a.gleg_ld + i] = gmu;
+        else a.g_arm[(int64_t)r * a.garm_ld + (i - a.n_leg)] = gmu;
+        gstd[i] = glp[c] * ((d * d) / (sg * sg * sg) - 1.0f / sg) - a.c_ent * inv2m / sg;
+      }
+    }
+    // value loss PPO:209-216
+    float gv[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float v = a.value[2 * r + c], vo = a.old_values[2 * src + c], R = a.returns[2 * src + c];
+      const float l1 = (v - R) * (v - R);
+      if (a.clipped_value) {
+        const float dvo = v - vo;
+        const float vc = vo + fminf(fmaxf(dvo, -a.clip), a.clip);
+        const float l2 = (vc - R) * (vc - R);
+        const bool inside = dvo >= -a.clip && dvo <= a.clip;
+        l_val += fmaxf(l1, l2);
+        const float g1 = 2.0f * (v - R), g2 = inside ? 2.0f * (vc - R) : 0.0f;
+        gv[c] = l1 > l2 ? g1 : (l1 == l2 ? 0.5f * g1 + 0.5f * g2 : g2);
+      } else {
+        l_val += l1;
+        gv[c] = 2.0f * (v - R);
+      }
+      gv[c] *= a.c_value * inv2m;
+    }
+    a.g_vl[r] = gv[0];
+    a.g_va[r] = gv[1];
+    // privileged-latent regulariser PPO:174-177
+    float nrm = 0.0f;
+    for (int i = 0; i < a.latent; ++i) {
+      const float d = a.zp[(int64_t)r * a.zld + i] - a.zh[(int64_t)r * a.zld + i];
+      nrm += d * d;
+    }
+    nrm = sqrtf(nrm);
+    l_reg = nrm;
+    const float s = nrm > 0.0f ? a.c_reg * invm / nrm : 0.0f;
+    for (int i = 0; i < a.latent; ++i)
+      a.g_z[(int64_t)r * a.zld + i] = s * (a.zp[(int64_t)r * a.zld + i] - a.zh[(int64_t)r * a.zld + i]);
+  }
+  // block reductions -> one atomic per CTA per quantity
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float v4[4] = {l_surr * inv2m, l_val * inv2m, l_reg * invm, l_ent * inv2m};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s = warp_sum(v4[k]);
+    if (lane == 0) red[k][w] = s;
+  }
+  if (threadIdx.x < 32) sred[threadIdx.x] = 0.0f;
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(a.losses + threadIdx.x, (red[threadIdx.x][0] + red[threadIdx.x][1]) + (red[threadIdx.x][2] + red[threadIdx.x][3]));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i < a.n_act) {
+      float s = warp_sum(gstd[i]);
+      if (lane == 0) atomicAdd(&sred[i], s);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < a.n_act) atomicAdd(a.grad_std + threadIdx.x, sred[threadIdx.x]);
+}
+
+// DAgger loss PPO:273-276: mean_rows || sg(zp) - zh ||_2 ; writes d/d zh_pre (ELU' folded in)
+__global__ void __launch_bounds__(128) dagger_loss_kernel(const float* __restrict__ zp, const float* __restrict__ zh, int zld, int latent,
+                                                          float* __restrict__ g, float* __restrict__ loss, int rows) {
+  __shared__ float red[4];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.0f;
+  if (r < rows) {
+    float nrm = 0.0f;
+    for (int i = 0; i < latent; ++i) {
+      const float d = zp[(int64_t)r * zld + i] - zh[(int64_t)r * zld + i];
+      nrm += d * d;
+    }
+    nrm = sqrtf(nrm);
+    l = nrm / (float)rows;
+    const float s = nrm > 0.0f ? 1.0f / ((float)rows * nrm) : 0.0f;
+    for (int i = 0; i < latent; ++i) {
+      const float y = zh[(int64_t)r * zld + i];
+      g[(int64_t)r * zld + i] = -s * (zp[(int64_t)r * zld + i] - y) * (y > 0.0f ? 1.0f : y + 1.0f);
+    }
+  }
+  float s = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(loss, (red[0] + red[1]) + (red[2] + red[3]));
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+// Backward of one head: Linear(+ELU) x nl, then Linear -> out.  G_out = d/d(pre-activation of the
+// last layer) [rows, n_out].  Accumulates weight grads into `grad`, and adds the head's
+// contribution to d(backbone output) into dtrunk (beta_trunk; ELU' of the trunk applied if apply_dact).
+static int head_backward(const float* P, float* grad, RowMat G_out, int n_out, int nl, const int32_t* dims, const int64_t* ow,
+                         const int64_t* ob, float* const* acts, RowMat trunk, int trunk_dim, float* dtrunk, int beta_trunk,
+                         int apply_dact, float* dA, float* dB, int rows, cudaStream_t st) {
+  RowMat G = G_out;
+  int gout = n_out;
+  for (int l = nl; l >= 0; --l) {
+    const int in = l == 0 ? trunk_dim : dims[l - 1];
+    RowMat X = l == 0 ? trunk : rowmat(acts[l - 1], dims[l - 1]);
+    TRY(linear_bwd_weight(G, X, grad + ow[l], in, grad + ob[l], rows, gout, in, st));
+    if (l == 0) {
+      TRY(linear_bwd_data(G, P + ow[l], in, dtrunk, trunk_dim, rows, in, gout, apply_dact ? ACT_ELU : ACT_NONE, trunk, beta_trunk, st));
+    } else {
+      float* d = (l & 1) ? dA : dB;
+      TRY(linear_bwd_data(G, P + ow[l], in, d, in, rows, in, gout, ACT_ELU, X, 0, st));
+      G = rowmat(d, in);
+      gout = in;
+    }
+  }
+  return DWBC_OK;
+}
+
+}  // namespace dwbc
+
+using namespace dwbc;
+
+extern "C" int64_t dwbc_workspace_bytes(const DwbcNetCfg* net, int64_t rows) {
+  if (check_net(net) != DWBC_OK || rows <= 0) return -1;
+  return make_plan(*net, rows, nullptr).bytes;
+}
+
+extern "C" int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, const float* eps,
+                               int32_t hist_encoding, float* actions, float* values, float* log_prob, float* mean, float* sigma,
+                               int32_t rows, void* workspace, dwbc_stream_t stream) {
+  TRY(check_net(net));
+  if (!params || !obs || !eps || !actions || !values || !log_prob || !mean || !sigma || !workspace || rows <= 0) return DWBC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const DwbcNetCfg& n = *net;
+  Plan p = make_plan(n, rows, workspace);
+  const float* z;
+  int zld = (int)align_up(p.latent, 4);
+  if (hist_encoding) {
+    TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+    z = p.zh;
+  } else {
+    TRY(priv_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+    z = p.priv[n.n_priv_layers - 1];
+  }
+  TRY(actor_forward(n, params, obs, nullptr, obs_stride, rows, z, zld, p, st));
+  TRY(critic_forward(n, params, obs, nullptr, obs_stride, rows, p, values, st));
+  act_finalize_kernel<<<(rows + 127) / 128, 128, 0, st>>>(p.mean, p.mean_ld, params + n.off_std, eps, actions, log_prob, mean, sigma, rows,
+                                                           n.n_leg, n.n_leg + n.n_arm);
+  DWBC_LAUNCH_CHECK();
+  return DWBC_OK;
+}
+
+extern "C" int dwbc_critic_values(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, float* values,
+                                  int32_t rows, void* workspace, dwbc_stream_t stream) {
+  TRY(check_net(net));
+  if (!params || !obs || !values || !workspace || rows <= 0) return DWBC_ERR_ARG;
+  Plan p = make_plan(*net, rows, workspace);
+  return critic_forward(*net, params, obs, nullptr, obs_stride, rows, p, values, (cudaStream_t)stream);
+}
+
+extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* params, const DwbcStorage* s, const int64_t* idx, int32_t M,
+                                       const DwbcPpoHyper* hp, float* grad, float* losses_out, void* workspace, dwbc_stream_t stream) {
+  TRY(check_net(net));
+  if (!params || !s || !idx || !hp || !grad || !losses_out || !workspace || M <= 0) return DWBC_ERR_ARG;
+  if (!s->observations || !s->actions || !s->values || !s->returns || !s->advantages || !s->log_prob) return DWBC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const DwbcNetCfg& n = *net;
+  const float* P = params;
+  const int rows = M;
+  Plan p = make_plan(n, rows, workspace);
+  const int Lld = (int)align_up(p.latent, 4);
+  const int gleg_ld = (int)align_up(n.n_leg, 4), garm_ld = (int)align_up(n.n_arm, 4);
+  if (cudaMemsetAsync(grad, 0, sizeof(float) * n.num_params, st) != cudaSuccess) return DWBC_ERR_LAUNCH;
+
+  // forward (the reference evaluates the actor 3x and the priv encoder 3x per mini-batch,
+  // PPO:166,174,230; identical values, so each is evaluated once here)
+  TRY(priv_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));
+  TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));           // PPO:175-176 (no grad)
+  float* z = p.priv[n.n_priv_layers - 1];
+  TRY(actor_forward(n, P, s->observations, idx, s->obs_stride, rows, z, Lld, p, st));
+  TRY(critic_forward(n, P, s->observations, idx, s->obs_stride, rows, p, p.value, st));
+
+  LossArgs a{};
+  a.mean = p.mean; a.mean_ld = p.mean_ld; a.std = P + n.off_std; a.value = p.value; a.zp = z; a.zld = Lld; a.zh = p.zh;
+  a.actions = s->actions; a.old_logp = s->log_prob; a.old_values = s->values; a.returns = s->returns; a.adv = s->advantages; a.idx = idx;
+  a.g_leg = p.g_leg; a.gleg_ld = gleg_ld; a.g_arm = p.g_arm; a.garm_ld = garm_ld; a.g_vl = p.g_vl; a.g_va = p.g_va; a.g_z = p.g_z;
+  a.grad_std = grad + n.off_std; a.losses = losses_out;
+  a.rows = rows; a.n_leg = n.n_leg; a.n_act = n.n_leg + n.n_arm; a.latent = p.latent;
+  a.clip = hp->clip_param; a.c_value = hp->value_loss_coef; a.c_ent = hp->entropy_coef; a.c_reg = hp->priv_reg_coef; a.rho = hp->mixing_ratio;
+  a.clipped_value = hp->use_clipped_value_loss;
+  ppo_loss_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a);
+  DWBC_LAUNCH_CHECK();
+
+  // ---- critic backward ----
+  {
+    const int nb = n.n_critic_layers, tdim = n.critic_dims[nb - 1];
+    RowMat trunk = rowmat(p.cb[nb - 1], tdim);
+    TRY(head_backward(P, grad, rowmat(p.g_vl, 1), 1, n.n_leg_layers, n.leg_dims, n.off_cleg_w, n.off_cleg_b, p.cl, trunk, tdim, p.d2, 0, 0,
+                      p.d0, p.d1, rows, st));
+    TRY(head_backward(P, grad, rowmat(p.g_va, 1), 1, n.n_arm_layers, n.arm_dims, n.off_carm_w, n.off_carm_b, p.ca, trunk, tdim, p.d2, 1, 1,
+                      p.d0, p.d1, rows, st));
+    RowMat G = rowmat(p.d2, tdim);
+    int gout = tdim;
+    for (int l = nb - 1; l >= 0; --l) {
+      const int in = l == 0 ? n.num_prop + n.num_priv : n.critic_dims[l - 1];
+      RowMat X = l == 0 ? rowmat_gather(s->observations, idx, s->obs_stride) : rowmat(p.cb[l - 1], in);
+      TRY(linear_bwd_weight(G, X, grad + n.off_critic_w[l], in, grad + n.off_critic_b[l], rows, gout, in, st));
+      if (l > 0) {
+        float* d = (l & 1) ? p.d0 : p.d1;
+        TRY(linear_bwd_data(G, P + n.off_critic_w[l], in, d, in, rows, in, gout, ACT_ELU, X, 0, st));
+        G = rowmat(d, in);
+        gout = in;
+      }
+    }
+  }
+  // ---- actor backward ----
+  {
+    const int nb = n.n_actor_layers, tdim = n.actor_dims[nb - 1];
+    RowMat trunk = rowmat(p.ab[nb - 1], tdim);
+    TRY(head_backward(P, grad, rowmat(p.g_leg, gleg_ld), n.n_leg, n.n_leg_layers, n.leg_dims, n.off_aleg_w, n.off_aleg_b, p.al, trunk, tdim,
+                      p.d2, 0, 0, p.d0, p.d1, rows, st));
+    TRY(head_backward(P, grad, rowmat(p.g_arm, garm_ld), n.n_arm, n.n_arm_layers, n.arm_dims, n.off_aarm_w, n.off_aarm_b, p.aa, trunk, tdim,
+                      p.d2, 1, 1, p.d0, p.d1, rows, st));
+    RowMat G = rowmat(p.d2, tdim);
+    int gout = tdim;
+    for (int l = nb - 1; l >= 1; --l) {
+      const int in = n.actor_dims[l - 1];
+      RowMat X = rowmat(p.ab[l - 1], in);
+      TRY(linear_bwd_weight(G, X, grad + n.off_actor_w[l], in, grad + n.off_actor_b[l], rows, gout, in, st));
+      float* d = (l & 1) ? p.d0 : p.d1;
+      TRY(linear_bwd_data(G, P + n.off_actor_w[l], in, d, in, rows, in, gout, ACT_ELU, X, 0, st));
+      G = rowmat(d, in);
+      gout = in;
+    }
+    // backbone layer 0: input = cat([obs_prop, z])
+    const int in0 = n.num_prop + p.latent;
+    TRY(linear_bwd_weight(G, rowmat_gather(s->observations, idx, s->obs_stride), grad + n.off_actor_w[0], in0, grad + n.off_actor_b[0], rows,
+                          gout, n.num_prop, st));
+    TRY(linear_bwd_weight(G, rowmat(z, Lld), grad + n.off_actor_w[0] + n.num_prop, in0, nullptr, rows, gout, p.latent, st));
+    // dL/dz = (policy path) + (priv-reg path, already in g_z); then through the ELU of the encoder's last layer
+    TRY(linear_bwd_data(G, P + n.off_actor_w[0] + n.num_prop, in0, p.g_z, Lld, rows, p.latent, gout, ACT_ELU, rowmat(z, Lld), 1, st));
+    RowMat Gp = rowmat(p.g_z, Lld);
+    int gp = p.latent;
+    for (int l = n.n_priv_layers - 1; l >= 0; --l) {
+      const int in = l == 0 ? n.num_priv : n.priv_dims[l - 1];
+      const int ldin = (int)align_up(in, 4);
+      RowMat X = l == 0 ? rowmat_gather(s->observations + n.num_prop, idx, s->obs_stride) : rowmat(p.priv[l - 1], ldin);
+      TRY(linear_bwd_weight(Gp, X, grad + n.off_priv_w[l], in, grad + n.off_priv_b[l], rows, gp, in, st));
+      if (l > 0) {
+        float* d = (l & 1) ? p.d0 : p.d1;
+        TRY(linear_bwd_data(Gp, P + n.off_priv_w[l], in, d, ldin, rows, in, gp, ACT_ELU, X, 0, st));
+        Gp = rowmat(d, ldin);
+        gp = in;
+      }
+    }
+  }
+  return DWBC_OK;
+}
+
+extern "C" int dwbc_dagger_minibatch_grad(const DwbcNetCfg* net, const float* params, const DwbcStorage* s, const int64_t* idx, int32_t M,
+                                          float* grad, float* losses_out, void* workspace, dwbc_stream_t stream) {
+  TRY(check_net(net));
+  if (!params || !s || !s->observations || !idx || !grad || !losses_out || !workspace || M <= 0) return DWBC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const DwbcNetCfg& n = *net;
+  const float* P = params;
+  const int rows = M, T = n.num_hist;
+  Plan p = make_plan(n, rows, workspace);
+  const int L = p.latent, Lld = (int)align_up(L, 4);
+  if (cudaMemsetAsync(grad, 0, sizeof(float) * n.num_params, st) != cudaSuccess) return DWBC_ERR_LAUNCH;
+  if (cudaMemsetAsync(p.dhw1, 0, sizeof(float) * (20 * 128), st) != cudaSuccess) return DWBC_ERR_LAUNCH;
+  if (cudaMemsetAsync(p.dhw2, 0, sizeof(float) * (10 * 40), st) != cudaSuccess) return DWBC_ERR_LAUNCH;
+  if (cudaMemsetAsync(p.dhwl, 0, sizeof(float) * (32 * 36), st) != cudaSuccess) return DWBC_ERR_LAUNCH;
+  TRY(priv_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));             // PPO:273-274 (no grad)
+  TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));             // PPO:275
+  dagger_loss_kernel<<<(rows + 127) / 128, 128, 0, st>>>(p.priv[n.n_priv_layers - 1], p.zh, Lld, L, p.dzh, losses_out, rows);
+  DWBC_LAUNCH_CHECK();
+  // linear_output: zh = ELU(flat . Wl'^T + b)
+  RowMat G4 = rowmat(p.dzh, Lld);
+  TRY(linear_bwd_weight(G4, rowmat(p.hc2, 36), p.dhwl, 36, grad + n.off_hist_b[3], rows, L, 36, st));
+  TRY(linear_bwd_data(G4, p.hwl, 36, p.d0, 36, rows, 36, L, ACT_ELU, rowmat(p.hc2, 36), 0, st));    // d(conv2 pre-act) as [rows*3, 12]
+  // conv2
+  RowMat G3 = rowmat(p.d0, 12);
+  TRY(linear_bwd_weight(G3, rowmat_grouped(p.hc1, nullptr, 3, 80, 20), p.dhw2, 40, grad + n.off_hist_b[2], rows * 3, 10, 40, st));
+  TRY(linear_bwd_data(G3, p.hw2, 40, p.dh_a2, 40, rows * 3, 40, 10, ACT_NONE, RowMat{}, 0, st));
+  {
+    int64_t tot = (int64_t)rows * 4 * 20;
+    col2im_dact_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.dh_a2, p.hc1, p.dh_c1, rows, 4, 20, 20, 3, 2, 1);
+    DWBC_LAUNCH_CHECK();
+  }
+  // conv1
+  RowMat G2 = rowmat(p.dh_c1, 20);
+  TRY(linear_bwd_weight(G2, rowmat_grouped(p.hproj, nullptr, 4, (int64_t)T * 32, 64), p.dhw1, 128, grad + n.off_hist_b[1], rows * 4, 20, 128, st));
+  TRY(linear_bwd_data(G2, p.hw1, 128, p.dh_a1, 128, rows * 4, 128, 20, ACT_NONE, RowMat{}, 0, st));
+  {
+    int64_t tot = (int64_t)rows * T * 32;
+    col2im_dact_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.dh_a1, p.hproj, p.dh_proj, rows, T, 30, 32, 4, 4, 2);
+    DWBC_LAUNCH_CHECK();
+  }
+  // projection
+  RowMat G1 = rowmat(p.dh_proj, 32);
+  RowMat hist = rowmat_grouped(s->observations + (n.num_obs - T * n.num_prop), idx, T, s->obs_stride, n.num_prop);
+  TRY(linear_bwd_weight(G1, hist, grad + n.off_hist_w[0], n.num_prop, grad + n.off_hist_b[0], rows * T, 30, n.num_prop, st));
+  hist_unpack_grad_kernel<<<(20 * 128 + 255) / 256, 256, 0, st>>>(p.dhw1, p.dhw2, p.dhwl, grad + n.off_hist_w[1], grad + n.off_hist_w[2],
+                                                                   grad + n.off_hist_w[3], L);
+  DWBC_LAUNCH_CHECK();
+  return DWBC_OK;
+}

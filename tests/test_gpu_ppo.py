@@ -1,0 +1,222 @@
+"""GPU parity of the rsl_rl update path (GAE, ActorCritic forward, PPO loss/backward, clip+Adam,
+DAgger) through the C ABI, against the reference golden vectors and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dwbc_b200 import synth
+from oracle import ppo_oracle as PO
+from test_oracle_golden import golden_params, ppo_hp
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_alg(N, T, P, **over):
+    from dwbc_b200.actor_critic import FlatActorCritic
+    from dwbc_b200.ppo import FusedPPO
+    ac = FlatActorCritic(device="cuda:0", num_priv=24, num_hist=10, num_prop=76)
+    ac.load_state_dict(P)
+    hp = ppo_hp()
+    hp.update(over)
+    alg = FusedPPO(ac, device="cuda:0", **hp)
+    alg.init_storage(N, T, [860], [None], [18])
+    return alg
+
+
+def fill_storage(alg, g, inp, T):
+    dev = alg.device
+    s = alg.storage
+    s._obs_all.copy_(torch.from_numpy(inp["obs"]).to(dev))
+    for k, src in (("actions", "actions"), ("values", "values"), ("actions_log_prob", "log_prob"), ("returns", "returns"),
+                   ("advantages", "advantages"), ("rewards", "rewards")):
+        getattr(s, k).copy_(torch.from_numpy(g[src]).to(dev))
+    s.dones.copy_(torch.from_numpy(inp["dones"]).to(dev).unsqueeze(-1).to(torch.uint8))
+
+
+def test_gae_matches_reference_golden():
+    g = np.load(os.path.join(G, "ppo.npz"))
+    N, T, seed, _ = [int(x) for x in g["meta"]]
+    alg = make_alg(N, T, golden_params(g, seed))
+    inp = synth.rollout_inputs(N, T, 860, seed)
+    fill_storage(alg, g, inp, T)
+    alg.storage.returns.zero_()
+    alg.storage.advantages.zero_()
+    alg.storage.compute_returns(torch.from_numpy(g["last_values"]).cuda(), 0.99, 0.95)
+    np.testing.assert_allclose(alg.storage.returns.cpu().numpy(), g["returns"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(alg.storage.advantages.cpu().numpy(), g["advantages"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("N,T", [(4096, 40), (8192, 24), (37, 5)])
+def test_gae_matches_oracle_full_size(N, T):
+    from dwbc_b200.storage import FusedRolloutStorage
+    s = FusedRolloutStorage(N, T, [8], [None], [18], "cuda:0")
+    rew = torch.from_numpy(synth.normal(1, 1, (T, N, 2)))
+    val = torch.from_numpy(synth.normal(1, 2, (T, N, 2)))
+    dones = torch.from_numpy(synth.bernoulli(1, 3, (T, N, 1), 0.05)).to(torch.uint8)
+    last = torch.from_numpy(synth.normal(1, 4, (N, 2)))
+    s.rewards.copy_(rew.cuda()); s.values.copy_(val.cuda()); s.dones.copy_(dones.cuda())
+    s.compute_returns(last.cuda(), 0.99, 0.95)
+    ret, adv = PO.compute_returns(rew, val, dones, last, 0.99, 0.95)
+    np.testing.assert_allclose(s.returns.cpu().numpy(), ret.numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(s.advantages.cpu().numpy(), adv.numpy(), rtol=1e-5, atol=2e-6)
+    a = s.advantages.double()
+    assert abs(float(a.mean())) < 1e-5 and abs(float(a.std()) - 1.0) < 1e-4          # size-independent property
+    # two-phase path (multi-GPU route): raw advantages + stats, then normalise
+    from dwbc_b200 import _lib as L
+    s.advantages.zero_(); s._stats.zero_()
+    L.check(L.lib().dwbc_gae(L.ptr(s.rewards), L.ptr(s.values), L.ptr(s.dones), L.ptr(last.cuda()), L.ptr(s.returns),
+                             L.ptr(s.advantages), L.ptr(s._stats), T, N, 0.99, 0.95, 0, L.stream_ptr()), "gae")
+    raw = (ret - val)
+    np.testing.assert_allclose(s.advantages.cpu().numpy(), raw.numpy(), rtol=1e-6, atol=1e-6)
+    assert float(s._stats[0]) == T * N * 2
+    L.check(L.lib().dwbc_normalize_advantages(L.ptr(s.advantages), L.ptr(s._stats), T * N * 2, L.stream_ptr()), "norm")
+    np.testing.assert_allclose(s.advantages.cpu().numpy(), adv.numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_policy_act_matches_reference_golden():
+    g = np.load(os.path.join(G, "ppo.npz"))
+    N, T, seed, _ = [int(x) for x in g["meta"]]
+    P = golden_params(g, seed)
+    alg = make_alg(N, T, P)
+    inp = synth.rollout_inputs(N, T, 860, seed)
+    obs = torch.from_numpy(inp["obs"]).cuda()
+    for t in (0, 1, T - 1):
+        mean_o = PO.actor_mean(P, obs[t].cpu())
+        eps = ((torch.from_numpy(g["actions"][t]) - mean_o) / P["std"]).cuda()
+        alg.storage.step = t
+        a = alg.act(obs[t], obs[t], False, eps=eps)
+        np.testing.assert_allclose(a.cpu().numpy(), g["actions"][t], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(alg.storage.values[t].cpu().numpy(), g["values"][t], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(alg.storage.actions_log_prob[t].cpu().numpy(), g["log_prob"][t], rtol=0, atol=1e-4)
+        if t == 0:
+            np.testing.assert_allclose(alg.storage.mu[0].cpu().numpy(), g["mu0"], rtol=0, atol=1e-5)
+        assert torch.equal(alg.storage.sigma[t], alg.actor_critic.std.expand(N, -1))
+    # time-out bootstrap (PPO:133-134) + dones storage (RS:102)
+    alg.storage.step = 0
+    alg.storage.values[0].copy_(torch.from_numpy(g["values"][0]).cuda())
+    alg.process_env_step(torch.from_numpy(inp["rew"][0]).cuda(), torch.from_numpy(inp["arm_rew"][0]).cuda(),
+                         torch.from_numpy(inp["dones"][0]).cuda(), {"time_outs": torch.from_numpy(inp["time_outs"][0]).cuda()})
+    np.testing.assert_allclose(alg.storage.rewards[0].cpu().numpy(), g["rewards"][0], rtol=0, atol=1e-6)
+    assert torch.equal(alg.storage.dones[0, :, 0].cpu(), torch.from_numpy(inp["dones"][0]).to(torch.uint8))
+    # student (history-encoder) rollout forward
+    Pd = golden_params(g, seed)
+    # dag_mu0 was produced with the post-update() parameters: rebuild them from param20 + min-std
+    flat20 = torch.from_numpy(g["param20"])
+    off = 0
+    for n in Pd:
+        k = Pd[n].numel()
+        Pd[n] = flat20[off:off + k].view_as(Pd[n]).clone()
+        off += k
+    alg2 = make_alg(N, T, Pd)
+    inp2 = synth.rollout_inputs(N, T, 860, seed + 1)
+    o0 = torch.from_numpy(inp2["obs"][0]).cuda()
+    eps2 = ((torch.from_numpy(g["dag_actions0"]) - torch.from_numpy(g["dag_mu0"])) / Pd["std"]).cuda()
+    alg2.act(o0, o0, True, eps=eps2)
+    np.testing.assert_allclose(alg2.storage.mu[0].cpu().numpy(), g["dag_mu0"], rtol=0, atol=1e-5)
+
+
+def _flat_ref(ac, vec):
+    """reference-ordered unpadded vector -> padded flat layout"""
+    out, off = {}, 0
+    for n, s in ac.manifest:
+        k = int(np.prod(s))
+        out[n] = torch.from_numpy(vec[off:off + k]).view(s)
+        off += k
+    return out
+
+
+def test_ppo_update_matches_reference_golden():
+    """BASELINE.json configs[0] on the GPU: losses, clipped gradient of step 1, post-Adam parameters
+    after step 1 and after the full 20-step update(), fp32 CUDA-core path.
+    Stated tolerances: grads 2e-6 abs (values ~1e-2), params 1e-6 after 1 step, 2e-5 after 20."""
+    g = np.load(os.path.join(G, "ppo.npz"))
+    N, T, seed, counter = [int(x) for x in g["meta"]]
+    alg = make_alg(N, T, golden_params(g, seed))
+    alg.counter = counter
+    fill_storage(alg, g, synth.rollout_inputs(N, T, 860, seed), T)
+    ac = alg.actor_critic
+    snap = {}
+
+    def on_step(k, when):
+        if k == 0 and when == "step":
+            snap["grad1"] = alg.grad.clone()        # clip_adam leaves the clipped gradient behind
+            snap["param1"] = ac.flat.clone()
+
+    res = alg.update(indices=torch.from_numpy(g["perm"]).cuda().long(), on_step=on_step)
+    ref = g["update_result"]
+    assert abs(res[0] - ref[0]) < 2e-5 * max(1, abs(ref[0])) and abs(res[1] - ref[1]) < 2e-5 and abs(res[5] - ref[5]) < 2e-5
+    assert res[3] == ref[3] and abs(res[6] - ref[6]) < 1e-7
+    g1, p1, p20 = _flat_ref(ac, g["grad1"]), _flat_ref(ac, g["param1"]), _flat_ref(ac, g["param20"])
+    got_g, got_p1, got_p20 = ac.unflat(snap["grad1"]), ac.unflat(snap["param1"]), ac.unflat(ac.flat)
+    for n, _ in ac.manifest:
+        np.testing.assert_allclose(got_g[n].cpu().numpy(), g1[n].numpy(), rtol=1e-3, atol=2e-6, err_msg="grad1 " + n)
+        np.testing.assert_allclose(got_p1[n].cpu().numpy(), p1[n].numpy(), rtol=0, atol=1e-6, err_msg="param1 " + n)
+        np.testing.assert_allclose(got_p20[n].cpu().numpy(), p20[n].numpy(), rtol=0, atol=2e-5, err_msg="param20 " + n)
+    assert alg.counter == counter + 1 and alg.storage.step == 0
+
+
+def test_dagger_update_matches_reference_golden():
+    g = np.load(os.path.join(G, "ppo.npz"))
+    N, T, seed, _ = [int(x) for x in g["meta"]]
+    P = golden_params(g, seed)
+    flat20, off = torch.from_numpy(g["param20"]), 0
+    for n in P:
+        k = P[n].numel()
+        P[n] = flat20[off:off + k].view_as(P[n]).clone()
+        off += k
+    alg = make_alg(N, T, P)
+    inp2 = synth.rollout_inputs(N, T, 860, seed + 1)
+    alg.storage._obs_all.copy_(torch.from_numpy(inp2["obs"]).cuda())
+    loss = alg.update_dagger(indices=torch.from_numpy(g["dag_perm"]).cuda().long())
+    assert abs(loss - float(g["dag_loss"][0])) < 2e-5
+    ref = _flat_ref(alg.actor_critic, g["dag_params"])
+    got = alg.actor_critic.unflat(alg.actor_critic.flat)
+    for n, _ in alg.actor_critic.manifest:
+        np.testing.assert_allclose(got[n].cpu().numpy(), ref[n].numpy(), rtol=0, atol=2e-5, err_msg=n)
+
+
+def test_minibatch_grad_matches_oracle_autograd_large():
+    """M = 8192 rows (oracle autograd on CPU): unclipped gradient of one mini-batch."""
+    N, T, seed = 1024, 8, 21
+    manifest = PO.param_manifest()
+    vals = synth.policy_params(manifest, seed)
+    P = {n: (torch.tensor([[0.8, 1.0, 1.0] * 4 + [1.0] * 6]) if v is None else torch.from_numpy(v).clone()) for (n, _), v in zip(manifest, vals)}
+    alg = make_alg(N, T, P, num_mini_batches=1, num_learning_epochs=1)
+    alg.counter = 1500
+    inp = synth.rollout_inputs(N, T, 860, seed)
+    obs = torch.from_numpy(inp["obs"])
+    st = dict(observations=obs[:T], actions=torch.from_numpy(synth.normal(seed, 50, (T, N, 18))),
+              values=torch.from_numpy(synth.normal(seed, 51, (T, N, 2))), returns=torch.from_numpy(synth.normal(seed, 52, (T, N, 2))),
+              actions_log_prob=torch.from_numpy(synth.normal(seed, 53, (T, N, 2), -20.0, 1.0)),
+              advantages=torch.from_numpy(synth.normal(seed, 54, (T, N, 2))))
+    s = alg.storage
+    s._obs_all.copy_(obs.cuda())
+    for k in ("actions", "values", "returns", "actions_log_prob", "advantages"):
+        getattr(s, k).copy_(st[k].cuda())
+    idx = torch.from_numpy(np.argsort(synth.uniform(seed, 60, (N * T,)))).long()
+    hp = ppo_hp()
+    for n in P:
+        P[n].requires_grad_(True)
+    loss, info = PO.minibatch_loss(P, PO.gather(st, idx), hp, 1500)
+    loss.backward()
+    import ctypes as C
+    from dwbc_b200 import _lib as L
+    ac = alg.actor_critic
+    h = alg._fill_hp()
+    alg._losses.zero_()
+    L.check(L.lib().dwbc_ppo_minibatch_grad(C.addressof(ac.net_cfg), L.ptr(ac.flat), s.c_struct_ptr(), L.ptr(idx.cuda()), N * T,
+                                            C.addressof(h), L.ptr(alg.grad), L.ptr(alg._losses), L.ptr(alg._workspace(N * T)),
+                                            L.stream_ptr()), "grad")
+    got = ac.unflat(alg.grad)
+    for n in P:
+        ref = P[n].grad if P[n].grad is not None else torch.zeros_like(P[n])
+        scale = max(float(ref.abs().max()), 1e-6)
+        err = float((got[n].cpu() - ref).abs().max()) / scale
+        assert err < 2e-3, (n, err)
+    ls = alg._losses.cpu()
+    assert abs(float(ls[0]) - float(info["surrogate"])) < 1e-4 * max(1.0, abs(float(info["surrogate"])))
+    assert abs(float(ls[1]) - float(info["value"])) < 1e-4 * max(1.0, abs(float(info["value"])))
+    assert abs(float(ls[2]) - float(info["priv_reg"])) < 1e-4
