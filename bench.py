@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the widowGo1 hot path (BASELINE.json metric).
+
+One "step" = one PPO iteration over one batch of synthetic sim-state tensors:
+  T=40 x [ policy act -> (synthetic physics stand-in) -> fused post-physics step -> reward store ]
+  -> critic bootstrap + GAE -> update() (5 epochs x 4 mini-batches of M = N*T/4 rows).
+`value` = world * N * T / iteration time, inputs already resident in HBM.
+`e2e`   = the same through the public API with HOST sim-state buffers: every env step copies that
+          step's six Isaac-Gym-layout tensors from pinned host memory and reads rewards/dones back.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference path on host cores
+
+Multi-GPU: launched by torch.distributed.run, one rank per GPU, 4096 envs per rank (weak scaling);
+one NCCL all-reduce of the flat gradient per PPO mini-batch + one of the advantage statistics.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_ENVS, T_STEPS = 4096, 40
+K1_BYTES_PER_ENV = 10653            # SURVEY.md section 8d, reference buffer semantics
+HP = dict(value_loss_coef=1.0, use_clipped_value_loss=True, clip_param=0.2, entropy_coef=0.0, num_learning_epochs=5,
+          num_mini_batches=4, learning_rate=2e-4, gamma=0.99, lam=0.95, max_grad_norm=1.0,
+          min_policy_std=[[0.15, 0.25, 0.25] * 4 + [0.2] * 3 + [0.05] * 3], mixing_schedule=[1.0, 0, 1],
+          priv_reg_coef_schedual=[0, 1, 1000, 1000])
+INIT_STD = [[0.8, 1.0, 1.0] * 4 + [1.0] * 6]
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, device, rank, n_envs=N_ENVS, T=T_STEPS, world=1, group=None, host_inputs=False):
+        import envstate as E
+        from dwbc_b200 import synth
+        from dwbc_b200.actor_critic import FlatActorCritic
+        from dwbc_b200.env import FusedWidowGo1Core
+        from dwbc_b200.ppo import FusedPPO
+        self.device, self.N, self.T, self.world = device, n_envs, T, world
+        p = E.make_params("flat", n_envs)
+        st = synth.initial_env_state(p, 100 + rank)
+        st.update(synth.sim_state(p, 100 + rank, 0, rp_sigma=0.05, z_lo=0.327))
+        self.p = p
+        self.env = FusedWidowGo1Core(p, device, state=st, seed=1000 + rank, sync_stats=False)
+        self.env.update_command_curriculum()
+        ac = FlatActorCritic(device=device, seed=0, init_std=INIT_STD, num_priv=24, num_hist=10, num_prop=76)  # same params on all ranks
+        self.alg = FusedPPO(ac, device=device, world_size=world, process_group=group, **HP)
+        self.alg.init_storage(n_envs, T, [p.num_obs], [None], [p.num_actions])
+        self.alg.counter = 1500           # priv-reg coef 0.5, mixing ratio 1.0: every loss branch active
+        self.alg.generator = torch.Generator(device=device)
+        self.alg.generator.manual_seed(7 + rank)
+        # ---- synthetic physics stand-in: T distinct sim states (366 MB > L2), regenerated on device ----
+        g = torch.Generator(device=device)
+        g.manual_seed(31 + rank)
+        base = {k: torch.from_numpy(v).to(device) for k, v in synth.sim_state(p, 100 + rank, 1, rp_sigma=0.05, z_lo=0.327).items()}
+        self.pool = []
+        for t in range(T):
+            s = {}
+            for k in ("root_states", "dof_state", "rigid_body_state", "contact_forces", "force_sensor", "torques"):
+                noise = torch.randn(base[k].shape, device=device, generator=g) * 0.02
+                s[k] = (base[k] + noise * base[k].abs().clamp(min=0.05)).contiguous()
+            q = s["root_states"][:, 0, 3:7]
+            s["root_states"][:, 0, 3:7] = q / q.norm(dim=-1, keepdim=True)
+            self.pool.append(s)
+        self.sim_bytes = sum(v.numel() * 4 for v in self.pool[0].values())
+        self.host_inputs = host_inputs
+        if host_inputs:
+            self.host_pool = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in self.pool]
+            self.dev_in = {k: torch.empty_like(v) for k, v in self.pool[0].items()}
+            self.env.bind_sim(**self.dev_in)
+            self.host_out = torch.empty(n_envs, 3, dtype=torch.float32).pin_memory()
+            self.dev_out = torch.empty(n_envs, 3, device=device)
+        self.k1_events = []
+        self.env.set_obs_target(self.alg.storage.obs_row(0))
+        self.obs = self.alg.storage.obs_row(0)
+        self.last = None
+
+    def iteration(self, time_k1=False):
+        env, alg, T = self.env, self.alg, self.T
+        obs = self.obs
+        if obs.data_ptr() != alg.storage.obs_row(0).data_ptr():
+            alg.storage.obs_row(0).copy_(obs)            # carry obs_T of the previous iteration into row 0
+            obs = alg.storage.obs_row(0)
+        for t in range(T):
+            actions = alg.act(obs, obs, False)
+            # --- physics stand-in: Isaac Gym would simulate and refresh these tensors in place ---
+            if self.host_inputs:
+                for k, dst in self.dev_in.items():
+                    dst.copy_(self.host_pool[t][k], non_blocking=True)
+            else:
+                env.bind_sim(**self.pool[t])
+            env.set_obs_target(alg.storage.obs_row(t + 1))
+            env.pre_physics_step(actions)
+            if time_k1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                env.post_physics_step()
+                e1.record()
+                self.k1_events.append((e0, e1))
+            else:
+                env.post_physics_step()
+            obs = env.obs_buf
+            alg.process_env_step(env.rew_buf, env.arm_rew_buf, env.reset_buf, env.extras)
+            if self.host_inputs:                      # the step's result goes back to the host
+                self.dev_out[:, 0], self.dev_out[:, 1], self.dev_out[:, 2] = env.rew_buf, env.arm_rew_buf, env.reset_buf.float()
+                self.host_out.copy_(self.dev_out, non_blocking=True)
+        alg.compute_returns(obs)
+        self.last = alg.update()
+        self.obs = obs
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback on the product path)"
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    from dwbc_b200 import _lib as L
+    lib = L.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(w, steps, time_k1=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.dwbc_launch_count()
+        e0.record()
+        for _ in range(steps):
+            w.iteration(time_k1)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), lib.dwbc_launch_count() - l0
+
+    w = Workload(device, rank, world=world, group=group)
+    for _ in range(max(args.warmup, 3)):
+        w.iteration()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(w, args.steps, time_k1=True)
+    clocks = sampler.finish() if sampler else None
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in w.k1_events])) if w.k1_events else None
+    value = world * w.N * w.T * args.steps / (ms / 1e3)
+
+    # ---- e2e: host sim-state buffers, H2D every env step, D2H of the step result ----
+    we = Workload(device, rank, world=world, group=group, host_inputs=True)
+    for _ in range(3):
+        we.iteration()
+    ems, _ = timed(we, args.steps)
+    e2e = world * we.N * we.T * args.steps / (ems / 1e3)
+
+    # ---- PPO update() alone on the resident rollout storage (second half of BASELINE's metric) ----
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(3):
+        w.alg.update()
+    u1.record()
+    barrier()
+    upd = torch.tensor([u0.elapsed_time(u1) / 3], device=device)
+    if world > 1:
+        dist.all_reduce(upd, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        pk, src = peaks()
+        achieved = w.N * K1_BYTES_PER_ENV / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tfile):
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        line = {
+            "metric": "env-steps/sec (widowGo1, 4096 envs/GPU)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "widowGo1 flat terrain, 4096 envs/GPU, T=40 rollout + GAE + PPO update (5 epochs x 4 mini-batches)",
+                       "envs_per_gpu": w.N, "rollout_steps": w.T, "mini_batch_rows": w.N * w.T // 4, "n_obs": 860,
+                       "mlp_path": "fp32 CUDA-core tile GEMM", "rng": "in-kernel Philox",
+                       "cache": "inputs_larger_than_L2 (sim-state pool %d MB + rollout obs %d MB per GPU)" %
+                                (w.sim_bytes * w.T // 2**20, (w.T + 1) * w.N * 860 * 4 // 2**20),
+                       "parallelism": f"env-sharded dp{world}"},
+            "ppo_update_ms": float(upd), "ppo_minibatch_ms": float(upd) / 20, "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(we.sim_bytes * we.T), "d2h_bytes_per_step": int(we.N * 12 * we.T),
+                    "ms_per_step": ems / args.steps},
+            "roofline": {"kernel": "env_step_kernel (fused post-physics, K1)", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": src,
+                         "us_per_launch": k1_ms * 1e3, "algorithmic_bytes_per_launch": w.N * K1_BYTES_PER_ENV},
+            "clocks": clocks,
+        }
+        torch.cuda.synchronize()
+        line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference; the reference itself is Python under /root/reference
+# and cannot travel to the GPU box)
+# ------------------------------------------------------------------------------------------------
+def make_oracle_iteration(n_envs, T, seed=100):
+    import envstate as E
+    from dwbc_b200 import synth
+    from oracle import ppo_oracle as PO
+    from oracle.pipeline import OracleIteration
+    p = E.make_params("flat", n_envs)
+    st = synth.initial_env_state(p, seed)
+    st.update(synth.sim_state(p, seed, 0, rp_sigma=0.05, z_lo=0.327))
+    manifest = PO.param_manifest()
+    vals = synth.policy_params(manifest, 0)
+    P = {n: (torch.tensor(INIT_STD) if v is None else torch.from_numpy(v).clone()) for (n, _), v in zip(manifest, vals)}
+    sims = [synth.sim_state(p, seed, t, rp_sigma=0.05, z_lo=0.327) for t in range(1, 5)]
+    tabs = [torch.from_numpy(synth.rand_table(p, seed, t)) for t in range(1, 5)]
+    return OracleIteration(p, E.oracle_state(p, st), E.runtime(p), P, dict(HP), lambda t: sims[t % 4], lambda t: tabs[t % 4], T)
+
+
+def pick_threads(n_envs=256):
+    """torch CPU intra-op threading is counter-productive past a point for these op sizes (128
+    OpenMP threads were 30x SLOWER than 8 on the GPU box's host): probe a short slice of the
+    workload at several thread counts up to all cores and keep the fastest, i.e. give the CPU arm
+    its best configuration.  Returns (threads_used, host_cores)."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        it = make_oracle_iteration(n_envs, 2)
+        it.hp = dict(it.hp, num_learning_epochs=1, num_mini_batches=1)
+        it.run()
+        t0 = time.perf_counter()
+        it.run()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+        if dt > 4 * best_t:
+            break
+    torch.set_num_threads(best)
+    return best, cores
+
+
+def cpu_baseline(args, n_envs=256):
+    cores, host_cores = pick_threads(n_envs)
+    it = make_oracle_iteration(n_envs, T_STEPS)
+    it.run()
+    t0 = time.perf_counter()
+    r = it.run()
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * T_STEPS / dt, "unit": "env-steps/s", "cores": cores, "host_cores": host_cores, "kind": "port",
+            "sample": f"one full PPO iteration of the oracle port at {n_envs} envs x {T_STEPS} steps (1/{N_ENVS // n_envs} of the workload), "
+                      f"{dt:.2f} s: rollout {r['rollout']:.2f} s, GAE {r['gae']:.3f} s, update {r['update']:.2f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_envs = 256
+    cores, host_cores = pick_threads(n_envs)
+    it = make_oracle_iteration(n_envs, T_STEPS)
+    for _ in range(args.warmup):
+        it.run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        it.run()
+    dt = time.perf_counter() - t0
+    value = n_envs * T_STEPS * args.steps / dt
+    sample = f"each step = one full PPO iteration at {n_envs} envs x {T_STEPS} steps (1/{N_ENVS // n_envs} of the 4096-env workload) on {cores} torch threads (fastest of a probe up to all {host_cores} host cores)"
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/sec (widowGo1, 4096 envs/GPU)", "value": value, "unit": "env-steps/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "widowGo1 flat terrain, T=40 rollout + GAE + PPO update (5 epochs x 4 mini-batches), CPU torch fp32",
+                   "envs": n_envs, "rollout_steps": T_STEPS},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdwbc.so")
 
 ABI_VERSION = 1
-MAX_DOF, MAX_TERMS, MAX_IDX, MAX_SLOTS, NUM_METRICS, RAND_COLS, MAX_LAYERS = 24, 24, 8, 64, 10, 104, 4
+MAX_DOF, MAX_TERMS, MAX_IDX, MAX_SLOTS, NUM_METRICS, RAND_COLS, MAX_LAYERS = 24, 40, 8, 64, 10, 104, 4
 GS, DS = 28, 72
 GS_COL = dict(commands=0, goal_timer=3, traj_timesteps=4, traj_total_timesteps=5, ee_start_sphere=6, ee_goal_sphere=9,
               ee_goal_cart=12, curr_ee_goal_sphere=15, curr_ee_goal_cart=18, ee_goal_delta_orn_euler=21, ee_goal_orn_euler=24)
@@ -128,7 +128,7 @@ _SIGS = {
     "dwbc_clip_adam_step": [vp, vp, vp, vp, i64, i64, vp, i32, vp, vp, vp],
     "dwbc_enforce_min_std": [vp, i64, vp, i32, vp],
 }
-EXPORTS = sorted(list(_SIGS) + ["dwbc_workspace_bytes", "dwbc_version", "dwbc_struct_sizes"])
+EXPORTS = sorted(list(_SIGS) + ["dwbc_workspace_bytes", "dwbc_version", "dwbc_struct_sizes", "dwbc_launch_count"])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -158,6 +158,7 @@ def lib():
     L.dwbc_workspace_bytes.argtypes = [vp, i64]
     L.dwbc_workspace_bytes.restype = i64
     L.dwbc_version.restype = C.c_char_p
+    L.dwbc_launch_count.restype = C.c_uint64
     L.dwbc_struct_sizes.argtypes = [C.POINTER(i64 * 6)]
     L.dwbc_struct_sizes.restype = None
     sizes = (i64 * 6)()

@@ -57,7 +57,7 @@ METRIC_NAMES = ["leg_energy_abs_sum", "tracking_lin_vel_x_l1", "tracking_ang_vel
                 "tracking_ee_cart", "tracking_ee_sphere", "tracking_ee_orn", "leg_action_l2",
                 "torque", "energy_square", "foot_contacts_z"]
 METRIC_ID = {n: i for i, n in enumerate(METRIC_NAMES)}
-MAX_TERMS = 24          # active terms per channel the ABI struct can carry
+MAX_TERMS = 40          # active terms per channel the ABI struct can carry
 
 # Column map of the dense per-step uniform table rand[N, RAND_COLS] (table mode) and of the
 # Philox counter space (in-kernel mode).  One column per reference torch_rand_float element.

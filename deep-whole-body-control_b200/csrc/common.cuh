@@ -5,8 +5,12 @@
 
 #include "dwbc.h"
 
+// every kernel launch of the library passes through one of these (host-side launch counter,
+// read back with dwbc_launch_count(); bench.py reports it as gpu_launches)
+extern unsigned long long dwbc_launch_counter;
 #define DWBC_LAUNCH_CHECK()                                   \
   do {                                                        \
+    ++dwbc_launch_counter;                                    \
     cudaError_t e__ = cudaGetLastError();                     \
     if (e__ != cudaSuccess) return DWBC_ERR_LAUNCH;           \
   } while (0)

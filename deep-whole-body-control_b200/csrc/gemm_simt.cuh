@@ -209,6 +209,7 @@ inline int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   else if (va) gemm_tile_kernel<kMode, true, false><<<grid, GT_THREADS, 0, st>>>(g);
   else if (vb) gemm_tile_kernel<kMode, false, true><<<grid, GT_THREADS, 0, st>>>(g);
   else gemm_tile_kernel<kMode, false, false><<<grid, GT_THREADS, 0, st>>>(g);
+  ++dwbc_launch_counter;
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
 

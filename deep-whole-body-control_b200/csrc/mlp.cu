@@ -185,6 +185,7 @@ static int hist_forward(const DwbcNetCfg& n, const float* P, const float* obs, c
   const int T = n.num_hist, L = p.latent, Lld = (int)align_up(L, 4);
   hist_pack_kernel<<<(20 * 128 + 255) / 256, 256, 0, st>>>(P + n.off_hist_w[1], P + n.off_hist_w[2], P + n.off_hist_w[3], p.hw1, p.hw2,
                                                            p.hwl, L);
+  dwbc_launch_counter += 3;
   // pad columns of the padded activation buffers are consumed by the next GEMM's K range
   zero_cols_kernel<<<(unsigned)(((int64_t)rows * T * 2 + 255) / 256), 256, 0, st>>>(p.hproj, (int64_t)rows * T, 32, 30);
   zero_cols_kernel<<<(unsigned)(((int64_t)rows * 3 * 2 + 255) / 256), 256, 0, st>>>(p.hc2, (int64_t)rows * 3, 12, 10);

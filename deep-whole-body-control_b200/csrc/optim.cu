@@ -83,6 +83,9 @@ extern "C" int dwbc_enforce_min_std(float* params, int64_t off_std, const float*
   return DWBC_OK;
 }
 
+unsigned long long dwbc_launch_counter = 0;
+extern "C" uint64_t dwbc_launch_count(void) { return dwbc_launch_counter; }
+
 extern "C" const char* dwbc_version(void) { return "dwbc-b200 0.1 (sm_100a, abi 1)"; }
 
 extern "C" void dwbc_struct_sizes(int64_t out[6]) {

@@ -35,7 +35,7 @@ enum {
 
 #define DWBC_ABI_VERSION 1
 #define DWBC_MAX_DOF 24
-#define DWBC_MAX_TERMS 24   /* active reward terms per channel */
+#define DWBC_MAX_TERMS 40   /* active reward terms per channel */
 #define DWBC_MAX_IDX 8      /* penalised / termination contact bodies */
 #define DWBC_MAX_SLOTS 64   /* episode_sums + episode_metric_sums columns */
 #define DWBC_NUM_METRICS 10 /* WG:164 */
@@ -297,6 +297,8 @@ int dwbc_clip_adam_step(float* params, float* grad, float* adam_m, float* adam_v
 int dwbc_enforce_min_std(float* params, int64_t off_std, const float* min_std, int32_t n, dwbc_stream_t stream);
 
 const char* dwbc_version(void);
+/* number of kernels this library has launched in this process (host-side counter) */
+uint64_t dwbc_launch_count(void);
 /* sizeof(DwbcEnvCfg, DwbcEnvBuffers, DwbcStepArgs, DwbcNetCfg, DwbcPpoHyper, DwbcStorage): lets a
  * foreign-language binding verify its struct mirrors at load time. */
 void dwbc_struct_sizes(int64_t out[6]);
