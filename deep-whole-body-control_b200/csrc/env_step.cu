@@ -15,9 +15,9 @@
 // measured 6.57 TB/s.  Compiled with -fmad=false so that discrete decisions (collision
 // rejection, command dead-band, termination thresholds) see the same fp32 roundings as the
 // reference's unfused torch arithmetic.
-#include <math.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "env_math.cuh"
 
 namespace dwbc {
 
@@ -29,80 +29,6 @@ enum {
   S_ROOT = 0, S_DOF = 16, S_EE = 64, S_FS = 80, S_TQ = 104, S_ACT = 128, S_AH = 152, S_GS = 176, S_DS = 204,
   S_SUM = 276, S_PRIV = 340, S_PROP = 372, S_CF = 468, S_TOTAL = 532
 };
-
-struct V3 { float x, y, z; };
-__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-
-// isaacgym.torch_utils.quat_rotate_inverse (restated, oracle/torch_utils.py); q = xyzw
-__device__ __forceinline__ V3 quat_rotate_inverse(const float* q, V3 v) {
-  V3 qv = mk(q[0], q[1], q[2]);
-  float qw = q[3];
-  float s = 2.0f * (qw * qw) - 1.0f;
-  V3 c = cross(qv, v);
-  float d = ((qv.x * v.x + qv.y * v.y) + qv.z * v.z);
-  return mk((v.x * s - c.x * qw * 2.0f) + qv.x * d * 2.0f, (v.y * s - c.y * qw * 2.0f) + qv.y * d * 2.0f,
-            (v.z * s - c.z * qw * 2.0f) + qv.z * d * 2.0f);
-}
-__device__ __forceinline__ V3 quat_apply(const float* q, V3 v) {
-  V3 qv = mk(q[0], q[1], q[2]);
-  V3 t = cross(qv, v);
-  t = mk(t.x * 2.0f, t.y * 2.0f, t.z * 2.0f);
-  V3 c = cross(qv, t);
-  return mk((v.x + q[3] * t.x) + c.x, (v.y + q[3] * t.y) + c.y, (v.z + q[3] * t.z) + c.z);
-}
-__device__ __forceinline__ void euler_from_quat(const float* q, float& roll, float& pitch, float& yaw) {
-  float x = q[0], y = q[1], z = q[2], w = q[3];
-  roll = atan2f(2.0f * (w * x + y * z), 1.0f - 2.0f * (x * x + y * y));
-  pitch = asinf(fminf(fmaxf(2.0f * (w * y - z * x), -1.0f), 1.0f));
-  yaw = atan2f(2.0f * (w * z + x * y), 1.0f - 2.0f * (y * y + z * z));
-}
-__device__ __forceinline__ V3 sphere2cart(V3 s) {
-  float proj = s.x * cosf(s.y);
-  return mk(proj * cosf(s.z), proj * sinf(s.z), s.x * sinf(s.y));
-}
-__device__ __forceinline__ V3 cart2sphere(V3 c) {
-  float l = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
-  return mk(l, asinf(c.z / l), atan2f(c.y, c.x));
-}
-// torch.remainder(a + pi, 2 pi) - pi  (fmod-based, like ATen)
-__device__ __forceinline__ float wrap_pi(float a) {
-  const float PI = 3.14159265358979323846f, TWO_PI = 6.28318530717958647692f;
-  float r = fmodf(a + PI, TWO_PI);
-  if (r != 0.0f && r < 0.0f) r += TWO_PI;
-  return r - PI;
-}
-// torch.lerp
-__device__ __forceinline__ float lerpf(float a, float b, float w) {
-  float d = b - a;
-  return (w < 0.5f) ? a + w * d : b - d * (1.0f - w);
-}
-__device__ __forceinline__ V3 lerp3(V3 a, V3 b, float w) { return mk(lerpf(a.x, b.x, w), lerpf(a.y, b.y, w), lerpf(a.z, b.z, w)); }
-__device__ __forceinline__ float clipf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
-__device__ __forceinline__ float4 clip4(float4 v, float c) {
-  return make_float4(clipf(v.x, -c, c), clipf(v.y, -c, c), clipf(v.z, -c, c), clipf(v.w, -c, c));
-}
-
-struct Rng {
-  const float* table;
-  uint64_t seed, step;
-  int env;
-  __device__ __forceinline__ float operator()(int col) const {
-    return table ? __ldg(table + (size_t)env * DWBC_RAND_COLS + col) : philox_uniform(seed, step, env, col);
-  }
-};
-
-// WG:1337-1342
-__device__ bool goal_collides(const DwbcEnvCfg& cfg, V3 start, V3 goal) {
-  bool hit = false;
-  for (int s = 0; s < cfg.n_collision_samples; ++s) {
-    V3 p = sphere2cart(lerp3(start, goal, cfg.collision_t[s]));
-    bool inside = (p.x < cfg.collision_upper[0] && p.y < cfg.collision_upper[1] && p.z < cfg.collision_upper[2]) &&
-                  (p.x > cfg.collision_lower[0] && p.y > cfg.collision_lower[1] && p.z > cfg.collision_lower[2]);
-    hit = hit || inside || (p.z < cfg.underground_limit);
-  }
-  return hit;
-}
 
 // WG:1316-1332 for one env; gs = staged goal_state row (all lanes compute, lane 0 commits)
 __device__ void resample_goal(const DwbcEnvCfg& cfg, const DwbcStepArgs& A, const Rng& rng, float* gs, float yaw,
@@ -192,7 +118,7 @@ __device__ float eval_term(int term, const TermCtx& c) {
     case DWBC_TERM_tracking_ang_vel_yaw_exp: {  // WG:1441-1444
       float e = fabsf(gs[2] - ds[DWBC_DS_BASE_ANG_VEL + 2]);
       if (l0) met[2] += e;
-      r = expf(-e / cfg.tracking_sigma);
+      r = nexp(-e / cfg.tracking_sigma);
     } break;
     case DWBC_TERM_tracking_ang_vel_yaw_l1: {  // WG:1437-1439
       float e = fabsf(gs[2] - ds[DWBC_DS_BASE_ANG_VEL + 2]);
@@ -206,17 +132,17 @@ __device__ float eval_term(int term, const TermCtx& c) {
     case DWBC_TERM_tracking_lin_vel_x_exp: {  // WG:1432-1435
       float e = fabsf(gs[0] - ds[DWBC_DS_BASE_LIN_VEL]);
       if (l0) met[1] += e;
-      r = expf(-e / cfg.tracking_sigma);
+      r = nexp(-e / cfg.tracking_sigma);
     } break;
     case DWBC_TERM_tracking_lin_vel_y_l2: { float e = gs[1] - ds[DWBC_DS_BASE_LIN_VEL + 1]; r = e * e; } break;  // WG:1446
     case DWBC_TERM_tracking_lin_vel_z_l2: { float e = gs[2] - ds[DWBC_DS_BASE_LIN_VEL + 2]; r = e * e; } break;  // WG:1449
     case DWBC_TERM_tracking_lin_vel: {  // WG:1422-1425
       float ex = gs[0] - ds[DWBC_DS_BASE_LIN_VEL], ey = gs[1] - ds[DWBC_DS_BASE_LIN_VEL + 1];
-      r = expf(-(ex * ex + ey * ey) / cfg.tracking_sigma);
+      r = nexp(-(ex * ex + ey * ey) / cfg.tracking_sigma);
     } break;
     case DWBC_TERM_tracking_ang_vel: {  // LR:886-889
       float e = gs[2] - ds[DWBC_DS_BASE_ANG_VEL + 2];
-      r = expf(-(e * e) / cfg.tracking_sigma);
+      r = nexp(-(e * e) / cfg.tracking_sigma);
     } break;
     case DWBC_TERM_torques: {  // WG:1460-1464
       r = warp_sum(tq * tq);
@@ -236,14 +162,14 @@ __device__ float eval_term(int term, const TermCtx& c) {
                  fabsf(s.y - gs[DWBC_GS_CURR_SPH + 1]) * cfg.sphere_error_scale[1]) +
                 fabsf(s.z - gs[DWBC_GS_CURR_SPH + 2]) * cfg.sphere_error_scale[2];
       if (l0) met[4] += e;
-      r = expf(-e / cfg.tracking_ee_sigma);
+      r = nexp(-e / cfg.tracking_ee_sigma);
     } break;
     case DWBC_TERM_tracking_ee_cart: {  // WG:1360-1366
       V3 t = quat_apply(ds + DWBC_DS_YAW_QUAT, mk(gs[DWBC_GS_CURR_CART], gs[DWBC_GS_CURR_CART + 1], gs[DWBC_GS_CURR_CART + 2]));
       float e = (fabsf(sm[S_EE] - (sm[S_ROOT] + t.x)) + fabsf(sm[S_EE + 1] - (sm[S_ROOT + 1] + t.y))) +
                 fabsf(sm[S_EE + 2] - (cfg.z_invariant_offset + t.z));
       if (l0) met[3] += e;
-      r = expf(-e / cfg.tracking_ee_sigma);
+      r = nexp(-e / cfg.tracking_ee_sigma);
     } break;
     case DWBC_TERM_tracking_ee_orn:
     case DWBC_TERM_tracking_ee_orn_ry: {  // WG:1368-1394
@@ -258,7 +184,7 @@ __device__ float eval_term(int term, const TermCtx& c) {
         e = fabsf(d0 * cfg.orn_error_scale[0]) + fabsf(d2 * cfg.orn_error_scale[2]);
         if (l0) met[5] += e;
       }
-      r = expf(-e / cfg.tracking_ee_sigma);
+      r = nexp(-e / cfg.tracking_ee_sigma);
     } break;
     case DWBC_TERM_lin_vel_z: r = ds[DWBC_DS_BASE_LIN_VEL + 2] * ds[DWBC_DS_BASE_LIN_VEL + 2]; break;  // LR:832
     case DWBC_TERM_ang_vel_xy:  // LR:836
@@ -398,7 +324,7 @@ env_step_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant__ 
     V3 bav = quat_rotate_inverse(q, mk(sm[S_ROOT + 10], sm[S_ROOT + 11], sm[S_ROOT + 12]));
     float r0, p0;
     euler_from_quat(q, r0, p0, yaw);
-    float cy = cosf(yaw * 0.5f), sy = sinf(yaw * 0.5f);
+    float cy = ncos(yaw * 0.5f), sy = nsin(yaw * 0.5f);
     __syncwarp();
     if (lane == 0) {
       ds[DWBC_DS_BASE_LIN_VEL] = blv.x; ds[DWBC_DS_BASE_LIN_VEL + 1] = blv.y; ds[DWBC_DS_BASE_LIN_VEL + 2] = blv.z;
@@ -600,6 +526,7 @@ env_step_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant__ 
     if (lane < na) ds[DWBC_DS_LAST_ACTIONS + lane] = sm[S_ACT + lane];
     if (lane < nd) ds[DWBC_DS_LAST_DOF_VEL + lane] = sm[S_DOF + 2 * lane + 1];
     if (lane < 6) ds[DWBC_DS_LAST_ROOT_VEL + lane] = sm[S_ROOT + 7 + lane];
+    if (lane == 7) ds[27] = 0.0f;  // DWBC_DS_OOB_AGE (v2 fast-path bookkeeping): v1 always clips, stay conservative
     __syncwarp();
   }
   // ---- 10. outputs -------------------------------------------------------------------------------
@@ -675,6 +602,10 @@ __global__ void pre_physics_actions_kernel(const float* __restrict__ pol, const 
 
 using namespace dwbc;
 
+int dwbc_launch_env_step_v2(const DwbcEnvCfg* cfg, const DwbcEnvBuffers* buf, const DwbcStepArgs* args, cudaStream_t st);
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 extern "C" int dwbc_post_physics_step(const DwbcEnvCfg* cfg, const DwbcEnvBuffers* buf, const DwbcStepArgs* args,
                                       dwbc_stream_t stream) {
   if (!cfg || !buf || !args) return DWBC_ERR_ARG;
@@ -698,6 +629,15 @@ extern "C" int dwbc_post_physics_step(const DwbcEnvCfg* cfg, const DwbcEnvBuffer
       !buf->obs_history || !buf->episode_sums || !buf->obs_buf || !buf->rew_buf || !buf->arm_rew_buf || !buf->reset_buf ||
       !buf->time_out_buf || !buf->episode_stats)
     return DWBC_ERR_ARG;
+  // v2 (32 envs per CTA, TMA bulk copies) whenever the shard is a multiple of 32 envs and every block is 16-B aligned
+  if (cfg->num_envs % 32 == 0 && aligned16(buf->root_states) && aligned16(buf->dof_state) && aligned16(buf->force_sensor) &&
+      aligned16(buf->torques) && aligned16(buf->actions) && aligned16(buf->action_history) && aligned16(buf->mass_params) &&
+      aligned16(buf->friction) && aligned16(buf->motor_strength) && aligned16(buf->goal_state) && aligned16(buf->derived_state) &&
+      aligned16(buf->episode_length) && aligned16(buf->obs_history) && aligned16(buf->episode_sums) && aligned16(buf->obs_buf) &&
+      !getenv("DWBC_ENV_KERNEL_V1")) {
+    int rc = dwbc_launch_env_step_v2(cfg, buf, args, (cudaStream_t)stream);
+    if (rc != DWBC_ERR_UNSUPPORTED) return rc;
+  }
   const int grid = (cfg->num_envs + ENV_WARPS - 1) / ENV_WARPS;
   env_step_kernel<<<grid, ENV_WARPS * 32, 0, (cudaStream_t)stream>>>(*cfg, *buf, *args);
   DWBC_LAUNCH_CHECK();

@@ -237,6 +237,8 @@ class FusedWidowGo1Core:
                 self._ds(k, t.shape[1]).copy_(t)
             elif k == "height_samples":
                 self.height_samples = T(v).to(torch.int16).contiguous()
+        if "obs_history_buf" in st:
+            self._derived_state[:, 27] = 0.0          # DWBC_DS_OOB_AGE: unknown history -> kernel takes the clipping path for H steps
         if "actions" not in st and "action_history_buf" in st:
             self.actions.copy_(self.action_history_buf[:, 1])      # [:, -action_delay-1] with AH = delay+2 (WG:541,1167)
 
