@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, rank, n_envs=N_ENVS, T=T_STEPS, world=1, group=None, host_inputs=False):
+    def __init__(self, device, rank, n_envs=N_ENVS, T=T_STEPS, world=1, group=None, host_inputs=False, precision="fp32"):
         import envstate as E
         from dwbc_b200 import synth
         from dwbc_b200.actor_critic import FlatActorCritic
@@ -94,7 +94,7 @@ class Workload:
         self.env = FusedWidowGo1Core(p, device, state=st, seed=1000 + rank, sync_stats=False)
         self.env.update_command_curriculum()
         ac = FlatActorCritic(device=device, seed=0, init_std=INIT_STD, num_priv=24, num_hist=10, num_prop=76)  # same params on all ranks
-        self.alg = FusedPPO(ac, device=device, world_size=world, process_group=group, **HP)
+        self.alg = FusedPPO(ac, device=device, world_size=world, process_group=group, precision=precision, **HP)
         self.alg.init_storage(n_envs, T, [p.num_obs], [None], [p.num_actions])
         self.alg.counter = 1500           # priv-reg coef 0.5, mixing ratio 1.0: every loss branch active
         self.alg.generator = torch.Generator(device=device)
@@ -190,7 +190,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), lib.dwbc_launch_count() - l0
 
-    w = Workload(device, rank, world=world, group=group)
+    w = Workload(device, rank, world=world, group=group, precision=args.precision)
     for _ in range(max(args.warmup, 3)):
         w.iteration()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -223,7 +223,7 @@ def run_ours(args):
     k1_ms = k1_queued()
 
     # ---- e2e: host sim-state buffers, H2D every env step, D2H of the step result ----
-    we = Workload(device, rank, world=world, group=group, host_inputs=True)
+    we = Workload(device, rank, world=world, group=group, host_inputs=True, precision=args.precision)
     for _ in range(3):
         we.iteration()
     ems, _ = timed(we, args.steps)
@@ -251,10 +251,10 @@ def run_ours(args):
         line = {
             "metric": "env-steps/sec (widowGo1, 4096 envs/GPU)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
             "config": {"workload": "widowGo1 flat terrain, 4096 envs/GPU, T=40 rollout + GAE + PPO update (5 epochs x 4 mini-batches)",
                        "envs_per_gpu": w.N, "rollout_steps": w.T, "mini_batch_rows": w.N * w.T // 4, "n_obs": 860,
-                       "mlp_path": "fp32 CUDA-core tile GEMM", "rng": "in-kernel Philox",
+                       "mlp_path": "fp32 CUDA-core tile GEMM" if args.precision == "fp32" else "TF32 tcgen05 GEMM (fp32 accumulate in TMEM)", "rng": "in-kernel Philox",
                        "cache": "inputs_larger_than_L2 (sim-state pool %d MB + rollout obs %d MB per GPU)" %
                                 (w.sim_bytes * w.T // 2**20, (w.T + 1) * w.N * 860 * 4 // 2**20),
                        "parallelism": f"env-sharded dp{world}"},
@@ -363,6 +363,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="ActorCritic GEMM path: fp32 CUDA cores (reference precision, default) or TF32 tcgen05 tensor cores")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

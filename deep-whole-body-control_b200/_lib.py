@@ -127,6 +127,7 @@ _SIGS = {
     "dwbc_dagger_minibatch_grad": [vp, vp, vp, vp, i32, vp, vp, vp, vp],
     "dwbc_clip_adam_step": [vp, vp, vp, vp, i64, i64, vp, i32, vp, vp, vp],
     "dwbc_enforce_min_std": [vp, i64, vp, i32, vp],
+    "dwbc_set_mlp_precision": [i32],
 }
 EXPORTS = sorted(list(_SIGS) + ["dwbc_workspace_bytes", "dwbc_version", "dwbc_struct_sizes", "dwbc_launch_count"])
 

@@ -8,9 +8,11 @@
 // (PPO:199-221) and its derivative w.r.t. the network outputs is one elementwise kernel.
 #include <math.h>
 
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace dwbc {
+
+int mlp_precision = 0;
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -637,4 +639,26 @@ extern "C" int dwbc_dagger_minibatch_grad(const DwbcNetCfg* net, const float* pa
                                                                    grad + n.off_hist_w[3], L);
   DWBC_LAUNCH_CHECK();
   return DWBC_OK;
+}
+
+// 0 = fp32 CUDA-core GEMMs (default, parity anchor), 1 = TF32 tcgen05 GEMMs
+extern "C" int dwbc_set_mlp_precision(int mode) {
+  if (mode != 0 && mode != 1) return DWBC_ERR_ARG;
+  mlp_precision = mode;
+  return DWBC_OK;
+}
+
+// Debug / test entry: one GEMM of the selected implementation on plain row-major device matrices.
+//   mode 0: Y[M,N] = act(X[M,K] W[N,K]^T + b)      mode 1: dX[M,N] = G[M,K] W[K,N]      mode 2: dW[M,N] += G[K,M]^T X[K,N], db += colsum(G)
+extern "C" int dwbc_debug_gemm(int mode, int tc, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc,
+                               const float* bias, float* dbias, int M, int N, int K, int act, dwbc_stream_t stream) {
+  const int saved = mlp_precision;
+  mlp_precision = tc;
+  int rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) rc = linear_fwd(rowmat(A, lda), Bm, ldb, bias, C, ldc, M, N, K, act, 0, st);
+  else if (mode == 1) rc = linear_bwd_data(rowmat(A, lda), Bm, ldb, C, ldc, M, N, K, ACT_NONE, RowMat{}, 0, st);
+  else rc = linear_bwd_weight(rowmat(A, lda), rowmat(Bm, ldb), C, ldc, dbias, K, M, N, st);
+  mlp_precision = saved;
+  return rc;
 }

@@ -57,7 +57,7 @@ class FusedPPO:
                  use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device="cuda:0",
                  mixing_schedule=(0.5, 2000, 4000), torque_supervision=False, torque_supervision_schedule=(0.1, 1000, 1000),
                  adaptive_arm_gains=False, min_policy_std=None, dagger_update_freq=20, priv_reg_coef_schedual=(0, 0, 0, 1),
-                 world_size=1, process_group=None):
+                 world_size=1, process_group=None, precision="fp32"):
         if torque_supervision or adaptive_arm_gains:
             raise L.DwbcError("torque_supervision / adaptive_arm_gains are disabled for widowGo1 (WGC:168,173) and outside the hot path")
         if schedule != "fixed":
@@ -75,6 +75,9 @@ class FusedPPO:
         self.dagger_update_freq = dagger_update_freq
         self.counter = 0
         self.world_size, self.process_group = world_size, process_group
+        if precision not in ("fp32", "tf32"):
+            raise L.DwbcError("precision must be 'fp32' (CUDA-core GEMMs, parity anchor) or 'tf32' (tcgen05 tensor cores)")
+        self.precision = precision
         ac = actor_critic
         self.optimizer = _AdamState(ac, 0, ac.num_params, learning_rate)                  # PPO:75
         hf, hc = ac.hist_range
@@ -100,6 +103,9 @@ class FusedPPO:
                         [torch.zeros(num_envs, 2, device=self.device) for _ in range(2)]
         self._workspace(max(num_envs, num_envs * num_transitions_per_env // self.num_mini_batches))
 
+    def _set_precision(self):
+        L.check(self._lib.dwbc_set_mlp_precision(1 if self.precision == "tf32" else 0), "dwbc_set_mlp_precision")
+
     def _workspace(self, rows):
         if self._ws is None or rows > self._ws_rows:
             nbytes = self._lib.dwbc_workspace_bytes(C.addressof(self.actor_critic.net_cfg), rows)
@@ -122,6 +128,7 @@ class FusedPPO:
     def act(self, obs, critic_obs=None, hist_encoding=False, eps=None):
         """PPO:115-127.  Outputs land directly in storage row `storage.step` when a storage exists."""
         ac, s = self.actor_critic, self.storage
+        self._set_precision()
         n = obs.shape[0]
         if eps is None:
             eps = self._eps.normal_(generator=self.generator)
@@ -162,6 +169,7 @@ class FusedPPO:
     def compute_returns(self, last_critic_obs):
         """PPO:148-150."""
         ac, s = self.actor_critic, self.storage
+        self._set_precision()
         obs = last_critic_obs.contiguous()
         L.check(self._lib.dwbc_critic_values(C.addressof(ac.net_cfg), L.ptr(ac.flat), L.ptr(obs), obs.stride(0),
                                              L.ptr(self._last_values), obs.shape[0], L.ptr(self._workspace(obs.shape[0])),
@@ -194,6 +202,7 @@ class FusedPPO:
     # ------------------------------------------------------------------ update (PPO:152-263)
     def update(self, indices=None, on_step=None):
         ac, s, hp = self.actor_critic, self.storage, self._fill_hp()
+        self._set_precision()
         if indices is None:
             indices, _ = s.draw_indices(self.num_mini_batches, self.generator)
         indices = indices.to(torch.int64).contiguous()
@@ -227,6 +236,7 @@ class FusedPPO:
     def update_dagger(self, indices=None):
         """PPO:265-291."""
         ac, s, hp = self.actor_critic, self.storage, self._fill_hp()
+        self._set_precision()
         if indices is None:
             indices, _ = s.draw_indices(self.num_mini_batches, self.generator)
         indices = indices.to(torch.int64).contiguous()

@@ -293,6 +293,10 @@ int dwbc_clip_adam_step(float* params, float* grad, float* adam_m, float* adam_v
                         const DwbcPpoHyper* hp, int32_t step, double* norm_scratch, float* grad_norm_out,
                         dwbc_stream_t stream);
 
+/* Precision of the ActorCritic GEMMs: 0 = fp32 CUDA cores (default; parity anchor), 1 = TF32 inputs / fp32 accumulate
+ * on the tcgen05 tensor cores. */
+int dwbc_set_mlp_precision(int mode);
+
 /* PPO.enforce_min_std (PPO:293-296): std = max(std, min_std). */
 int dwbc_enforce_min_std(float* params, int64_t off_std, const float* min_std, int32_t n, dwbc_stream_t stream);
 

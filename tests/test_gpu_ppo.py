@@ -222,3 +222,40 @@ def test_minibatch_grad_matches_oracle_autograd_large():
     assert abs(float(ls[0]) - float(info["surrogate"])) < 1e-4 * max(1.0, abs(float(info["surrogate"])))
     assert abs(float(ls[1]) - float(info["value"])) < 1e-4 * max(1.0, abs(float(info["value"])))
     assert abs(float(ls[2]) - float(info["priv_reg"])) < 1e-4
+
+
+def test_tf32_tensor_core_path_matches_reference_within_stated_tolerance():
+    """precision='tf32' (tcgen05, 10-bit mantissa inputs, fp32 accumulate) on BASELINE configs[0].
+    Stated tolerances: forward values / means 2e-2 abs, mean losses 2 % relative, clipped step-1 gradient within 5 % of its
+    own norm (||dg|| / ||g||), parameters after the 20-step update() within 20 * lr = 4e-3 (Adam moves each entry by at
+    most ~lr per step, so a sign flip of a tiny gradient costs at most 2*lr per step)."""
+    g = np.load(os.path.join(G, "ppo.npz"))
+    N, T, seed, counter = [int(x) for x in g["meta"]]
+    P = golden_params(g, seed)
+    alg = make_alg(N, T, P, precision="tf32")
+    inp = synth.rollout_inputs(N, T, 860, seed)
+    obs0 = torch.from_numpy(inp["obs"][0]).cuda()
+    mean_o = PO.actor_mean(P, obs0.cpu())
+    eps = ((torch.from_numpy(g["actions"][0]) - mean_o) / P["std"]).cuda()
+    alg.act(obs0, obs0, False, eps=eps)
+    np.testing.assert_allclose(alg.storage.mu[0].cpu().numpy(), g["mu0"], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(alg.storage.values[0].cpu().numpy(), g["values"][0], rtol=0, atol=2e-2)
+    alg.storage.step = 0
+    alg.counter = counter
+    fill_storage(alg, g, inp, T)
+    ac = alg.actor_critic
+    snap = {}
+
+    def on_step(k, when):
+        if k == 0 and when == "step":
+            snap["grad1"] = alg.grad.clone()
+
+    res = alg.update(indices=torch.from_numpy(g["perm"]).cuda().long(), on_step=on_step)
+    ref = g["update_result"]
+    assert abs(res[0] - ref[0]) < 2e-2 * abs(ref[0]) and abs(res[1] - ref[1]) < 2e-3 and abs(res[5] - ref[5]) < 2e-2 * abs(ref[5])
+    g1 = torch.cat([v.reshape(-1) for v in _flat_ref(ac, g["grad1"]).values()])
+    got = torch.cat([v.reshape(-1).cpu() for v in ac.unflat(snap["grad1"]).values()])
+    assert float((got - g1).norm() / g1.norm()) < 5e-2
+    p20 = torch.cat([v.reshape(-1) for v in _flat_ref(ac, g["param20"]).values()])
+    gotp = torch.cat([v.reshape(-1).cpu() for v in ac.unflat(ac.flat).values()])
+    assert float((gotp - p20).abs().max()) < 4e-3
