@@ -377,40 +377,4 @@ inline int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
 
-// precision mode of the ActorCritic GEMMs: 0 = fp32 CUDA cores (parity anchor), 1 = TF32 tcgen05 (defined in mlp.cu)
-extern int mlp_precision;
-
-template <int kMode>
-inline int dispatch_gemm(const GemmArgs& g, cudaStream_t st) {
-  if (mlp_precision == 1 && tc_shape_ok(kMode, g)) return launch_gemm_tc<kMode>(g, st);
-  return launch_gemm<kMode>(g, st);
-}
-
-// Y = act(beta*Y + X W^T + b)
-inline int linear_fwd(RowMat X, const float* W, int64_t ldw, const float* b, float* Y, int64_t ldy, int M, int N, int K,
-                      int act, int beta, cudaStream_t st) {
-  GemmArgs g{};
-  g.A = X; g.B = rowmat(W, ldw); g.C = Y; g.ldc = ldy; g.bias = b; g.act = act; g.beta = beta; g.M = M; g.N = N; g.K = K;
-  return dispatch_gemm<GEMM_FWD>(g, st);
-}
-// dX[M x Nin] = (beta*dX + G[M x Nout] W[Nout x Nin]) * act'(Xact)
-inline int linear_bwd_data(RowMat G, const float* W, int64_t ldw, float* dX, int64_t lddx, int M, int Nin, int Nout,
-                           int act, RowMat Xact, int beta, cudaStream_t st) {
-  GemmArgs g{};
-  g.A = G; g.B = rowmat(W, ldw); g.C = dX; g.ldc = lddx; g.act = act; g.Xact = Xact; g.beta = beta; g.M = M; g.N = Nin; g.K = Nout;
-  return dispatch_gemm<GEMM_BWD_DATA>(g, st);
-}
-// dW[Nout x Nin] += G^T X ; db += colsum(G)   (over `rows` rows)
-inline int linear_bwd_weight(RowMat G, RowMat X, float* dW, int64_t lddw, float* db, int rows, int Nout, int Nin, cudaStream_t st) {
-  GemmArgs g{};
-  g.A = G; g.B = X; g.C = dW; g.ldc = lddw; g.dbias = db; g.M = Nout; g.N = Nin; g.K = rows;
-  int tiles = ((Nout + GT_M - 1) / GT_M) * ((Nin + GT_N - 1) / GT_N);
-  int splits = (592 + tiles - 1) / tiles;                 // ~4 CTAs per SM over the whole grid
-  int chunk = (rows + splits - 1) / splits;
-  chunk = ((chunk + GT_K - 1) / GT_K) * GT_K;
-  if (chunk < 64) chunk = 64;
-  g.k_chunk = chunk;
-  return dispatch_gemm<GEMM_BWD_WGT>(g, st);
-}
-
 }  // namespace dwbc

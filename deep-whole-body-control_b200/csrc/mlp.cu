@@ -8,11 +8,15 @@
 // (PPO:199-221) and its derivative w.r.t. the network outputs is one elementwise kernel.
 #include <math.h>
 
-#include "gemm_tc.cuh"
+#include <stdlib.h>
+
+#include "gemm_tc2.cuh"
 
 namespace dwbc {
 
 int mlp_precision = 0;
+int tc_simple = 0;
+int tc_debug = 0;
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -645,6 +649,7 @@ extern "C" int dwbc_dagger_minibatch_grad(const DwbcNetCfg* net, const float* pa
 extern "C" int dwbc_set_mlp_precision(int mode) {
   if (mode != 0 && mode != 1) return DWBC_ERR_ARG;
   mlp_precision = mode;
+  tc_simple = getenv("DWBC_TC_SIMPLE") ? 1 : 0;
   return DWBC_OK;
 }
 
@@ -654,6 +659,8 @@ extern "C" int dwbc_debug_gemm(int mode, int tc, const float* A, int64_t lda, co
                                const float* bias, float* dbias, int M, int N, int K, int act, dwbc_stream_t stream) {
   const int saved = mlp_precision;
   mlp_precision = tc;
+  tc_simple = getenv("DWBC_TC_SIMPLE") ? 1 : 0;
+  tc_debug = getenv("DWBC_TC_DEBUG") ? atoi(getenv("DWBC_TC_DEBUG")) : 0;
   int rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0) rc = linear_fwd(rowmat(A, lda), Bm, ldb, bias, C, ldc, M, N, K, act, 0, st);
@@ -661,4 +668,8 @@ extern "C" int dwbc_debug_gemm(int mode, int tc, const float* A, int64_t lda, co
   else rc = linear_bwd_weight(rowmat(A, lda), rowmat(Bm, ldb), C, ldc, dbias, K, M, N, st);
   mlp_precision = saved;
   return rc;
+}
+
+extern "C" int dwbc_debug_set_tc_cycle_buffer(unsigned long long* dev_ptr) {
+  return cudaMemcpyToSymbol(g_tc_cycles, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
