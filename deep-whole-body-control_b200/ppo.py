@@ -20,6 +20,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+from . import shard
 from .actor_critic import FlatActorCritic
 from .storage import FusedRolloutStorage
 
@@ -191,13 +192,11 @@ class FusedPPO:
         h.priv_reg_coef, h.mixing_ratio = self.get_priv_reg_coef(), self.get_value_mixing_ratio()
         h.use_clipped_value_loss = int(self.use_clipped_value_loss)
         h.max_grad_norm, h.lr, h.beta1, h.beta2, h.adam_eps = self.max_grad_norm, self.learning_rate, 0.9, 0.999, 1e-8
-        h.grad_scale = 1.0 / self.world_size
+        h.grad_scale = shard.grad_scale(self.world_size)
         return h
 
     def _allreduce(self, first, count):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grad[first:first + count], group=self.process_group)
+        shard.allreduce_grad_(self.grad, first, count, self.world_size, self.process_group)
 
     # ------------------------------------------------------------------ update (PPO:152-263)
     def update(self, indices=None, on_step=None):

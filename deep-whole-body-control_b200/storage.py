@@ -16,6 +16,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+from . import shard
 
 
 class FusedRolloutStorage:
@@ -67,8 +68,7 @@ class FusedRolloutStorage:
                                    L.ptr(self.returns), L.ptr(self.advantages), L.ptr(self._stats), T, N, gamma, lam, int(fused),
                                    L.stream_ptr()), "dwbc_gae")
         if not fused:
-            import torch.distributed as dist
-            dist.all_reduce(self._stats, group=group)
+            shard.allreduce_adv_stats_(self._stats, world_size, group)
             L.check(self._lib.dwbc_normalize_advantages(L.ptr(self.advantages), L.ptr(self._stats), T * N * 2, L.stream_ptr()),
                     "dwbc_normalize_advantages")
 
