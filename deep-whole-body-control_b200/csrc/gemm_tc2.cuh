@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const GemmArgs 
 
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
-      tc_mbar_init(&sh.full[i], T2_PROD);   // (== T2_EPI: in the weight-gradient mode full[2] is signalled by the transposer warps)
-      tc_mbar_init(&sh.empty[i], (kMode == GEMM_BWD_WGT && i == 2) ? 1 : T2_EPI);
+      tc_mbar_init(&sh.full[i], T2_PROD);
+      // weight-gradient mode: a stage is released by the MMA commit plus, when a bias gradient is wanted, one lane of each of the 4 epilogue warps
+      tc_mbar_init(&sh.empty[i], kMode == GEMM_BWD_WGT ? (g.dbias != nullptr ? 5 : 1) : T2_EPI);
     }
     for (int i = 0; i < 2; ++i) { tc_mbar_init(&sh.tfull[i], 1); tc_mbar_init(&sh.tempty[i], T2_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -301,126 +302,133 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const GemmArgs 
     }
   } else {
     // ---------------- weight gradient ---------------------------------------------------------------------------------
-    // D[out x in] += G^T X over this CTA's slab of rows, 64 rows per chunk.  Both operands need the ROW index as the
-    // contraction (K) dimension, i.e. a transpose of the row-major sources:
-    //   warps 0-3 : cp.async the 64 G rows and 64 X rows of chunk c+1/c+2 into padded row-major raw tiles (2 stages);
-    //   warps 5-8 : transpose raw -> canonical K-major operand tiles in shared memory (thread = feature index, 4 scalar
-    //               LDS + one 16-byte STS per 4 rows, conflict free), accumulate the bias gradient in a register;
-    //   warp  4   : 8 tcgen05.mma per chunk into one TMEM accumulator; after the last chunk the transposer warps become
-    //               the epilogue and reduce the split-K partial into global memory with atomics.
+    // D[out x in] += G^T X over this CTA's slab of rows, 64 rows per chunk.  The contraction index is the ROW of the
+    // row-major sources, i.e. both operands are "MN-major".  For 32-bit operands tcgen05 supports exactly one MN-major
+    // shared-memory layout, SWIZZLE_128B_BASE32B (layout type 1; verified on B200 with tools/probes/mn_probe.cu; the
+    // no-swizzle MN-major form silently yields zeros for kind::tf32):
+    //   atom = 4 rows (k) x 32 features (128 B per row), 32-byte chunk c of row r stored at chunk c ^ (r & 3);
+    //   feature-atom stride (LBO) 512 B, row-atom stride (SBO) 4 x 512 B.
+    // A 16-byte piece of a source row stays a 16-byte piece, so the producers cp.async rows straight from global
+    // memory into the operand tiles: no transposition pass.
+    //   warps 0-3 : cp.async producers (3 stages of {G tile, X tile}, 32 KB each);
+    //   warp  4   : 8 tcgen05.mma (K = 8 rows each) per chunk into one TMEM accumulator;
+    //   warps 5-8 : bias gradient (column sums of the G tile, conflict-free LDS), then the split-K epilogue (atomics).
     const int Mo = g.M, Ni = g.N;
     const int nipad = (Ni + 15) & ~15;
-    constexpr int RAW = T2_WCH * T2_LDS;              // floats per raw operand tile [64][132]
-    float* raw[2] = {t2_smem, t2_smem + 2 * RAW};     // stage = {G tile, X tile}
-    float* canA = t2_smem + 4 * RAW;                  // [128 x 64] K-major
-    float* canB = canA + TC_M * T2_WCH;
+    constexpr int TILE = T2_WCH * 128;                // floats per operand tile: 64 rows x 128 features
     const int64_t k_begin = (int64_t)blockIdx.x * g.k_chunk;      // one slab per CTA (grid == items)
     const int64_t k_end = min((int64_t)g.K, k_begin + g.k_chunk);
     const int nch = (int)((k_end - k_begin + T2_WCH - 1) / T2_WCH);
-    // barrier roles in this mode: full[s]/empty[s] (s<2) = raw stage s; full[2] = canonical tiles ready; empty[2] = consumed
     if (warp < 4) {
       const int ptid = tid;
       const bool fastA = (vecA & 1) && (Mo & 3) == 0, fastB = (vecB & 1) && (Ni & 3) == 0;
       for (int c = 0; c < nch; ++c) {
-        const int s = c & 1;
+        const int s = c % 3;
         const int64_t k0 = k_begin + (int64_t)c * T2_WCH;
         const int nk = (int)min((int64_t)T2_WCH, k_end - k0);
         t2_pbar();
         if (ptid < T2_WCH) { sh.rowoff[ptid] = ptid < nk ? (g.A.row(k0 + ptid) - g.A.p) : 0; sh.rowoff[64 + ptid] = ptid < nk ? (g.B.row(k0 + ptid) - g.B.p) : 0; }
-        tc_mbar_wait(&sh.empty[s], ((c >> 1) & 1) ^ 1);
+        tc_mbar_wait(&sh.empty[s], ((c / 3) & 1) ^ 1);
         t2_pbar();
         for (int op = 0; op < 2; ++op) {
-          float* dst = raw[s] + op * RAW;
+          float* dst = t2_smem + (2 * s + op) * TILE;
           const float* base = op == 0 ? g.A.p : g.B.p;
           const int64_t* ro = sh.rowoff + 64 * op;
           const int ncol = op == 0 ? Mo : Ni;
           if (op == 0 ? fastA : fastB) {
-            const int cpr = ncol >> 2;                          // 16-byte chunks per row
+            const int cpr = ncol >> 2;                          // 16-byte pieces per row
             const uint32_t d0 = tc_smem_u32(dst);
+            const bool pow2 = (cpr & (cpr - 1)) == 0;
+            const int sh2 = 31 - __clz(cpr);
             for (int i = ptid; i < T2_WCH * cpr; i += T2_PROD) {
-              const int k = i / cpr, cc = i - k * cpr;
+              const int k = pow2 ? (i >> sh2) : i / cpr, cc = i - k * cpr;          // row, piece
               const float* src = k < nk ? base + ro[k] + 4 * cc : base;
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + (uint32_t)(k * T2_LDS + 4 * cc) * 4), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
+              const uint32_t off = (uint32_t)((cc >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((cc >> 1) & 3) ^ (k & 3)) << 5) + ((cc & 1) << 4));
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + off), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
             }
           } else {
             for (int i = ptid; i < T2_WCH * ncol; i += T2_PROD) {
-              const int k = i / ncol, cc = i - k * ncol;
-              dst[k * T2_LDS + cc] = k < nk ? base[ro[k] + cc] : 0.0f;
+              const int k = i / ncol, f = i - k * ncol;
+              const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
+              dst[off] = k < nk ? base[ro[k] + f] : 0.0f;
             }
           }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        t2_arrive(&sh.full[s]);
+        // asynchronous arrival: the stage is signalled when this thread's copies have landed, the producer moves on to the next stage
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.full[s])) : "memory");
+        if (ptid == 0) T2_STAMP(1 + c);
       }
     } else if (warp == 4) {
       if (lane == 0) {
-        const uint32_t idesc = tc_idesc(nipad, false, false);
-        const uint32_t a0 = tc_smem_u32(canA), b0 = tc_smem_u32(canB);
+        const uint32_t idesc = tc_idesc(nipad, true, true);
         for (int c = 0; c < nch; ++c) {
-          tc_mbar_wait(&sh.full[2], c & 1);
+          const int s = c % 3;
+          tc_mbar_wait(&sh.full[s], (c / 3) & 1);
+          tc_fence_async_smem();          // generic-proxy writes of the producers (made visible by the barrier) -> async proxy reads of the MMA
           tc_fence_after();
+          const uint32_t a0 = tc_smem_u32(t2_smem + (2 * s) * TILE), b0 = a0 + TILE * 4;
           for (int kk = 0; kk < T2_WCH; kk += 8) {
-            const uint64_t ad = tc_desc(a0 + (kk >> 2) * 128, 128, (T2_WCH >> 2) * 128);
-            const uint64_t bd = tc_desc(b0 + (kk >> 2) * 128, 128, (T2_WCH >> 2) * 128);
+            const uint64_t ad = tc_desc(a0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
+            const uint64_t bd = tc_desc(b0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
             tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || kk > 0) ? 1u : 0u);
           }
-          tc_commit(&sh.empty[2]);
+          tc_commit(&sh.empty[s]);
+          T2_STAMP(16 + c);
         }
         tc_commit(&sh.tfull[0]);
       }
     } else {
-      const int et = tid - (T2_PROD + 32);             // 0..127: the feature (operand row) this thread transposes
+      const int et = tid - (T2_PROD + 32);             // 0..127: output feature whose bias gradient / accumulator row this thread owns
       const int q = warp & 3;
       float bsum = 0.0f;
-      for (int c = 0; c < nch; ++c) {
-        const int s = c & 1;
-        tc_mbar_wait(&sh.full[s], (c >> 1) & 1);       // raw tiles landed
-        tc_mbar_wait(&sh.empty[2], (c & 1) ^ 1);       // canonical tiles consumed by the MMAs of chunk c-1
-        const float* rg = raw[s];
-        const float* rx = raw[s] + RAW;
-        {  // A(m = out feature et, k = row): canonical offset ((m/8)*16 + k/4)*32 + (m%8)*4 floats
-          float* dst = canA + ((size_t)(et >> 3) * (T2_WCH >> 2)) * 32 + (et & 7) * 4;
+      if (g.dbias != nullptr) {
+        const int fo = (et >> 5) * 128 + (et & 7);     // float offset of feature et inside row 0 of its atom (before the chunk swizzle)
+        const int c32 = (et & 31) >> 3;
+        for (int c = 0; c < nch; ++c) {
+          const int s = c % 3;
+          tc_mbar_wait(&sh.full[s], (c / 3) & 1);
+          const float* gt = t2_smem + (2 * s) * TILE;
           if (et < Mo) {
-#pragma unroll 4
-            for (int k4 = 0; k4 < T2_WCH / 4; ++k4) {
-              const float4 v = make_float4(rg[(4 * k4) * T2_LDS + et], rg[(4 * k4 + 1) * T2_LDS + et], rg[(4 * k4 + 2) * T2_LDS + et], rg[(4 * k4 + 3) * T2_LDS + et]);
-              bsum += (v.x + v.y) + (v.z + v.w);
-              *reinterpret_cast<float4*>(dst + k4 * 32) = v;
-            }
-          } else {
-            for (int k4 = 0; k4 < T2_WCH / 4; ++k4) *reinterpret_cast<float4*>(dst + k4 * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int k = 0; k < T2_WCH; ++k) bsum += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
           }
+          __syncwarp();
+          if (lane == 0) t2_arrive(&sh.empty[s]);
         }
-        if (et < nipad) {  // B(n = in feature et, k = row)
-          float* dst = canB + ((size_t)(et >> 3) * (T2_WCH >> 2)) * 32 + (et & 7) * 4;
-          if (et < Ni) {
-#pragma unroll 4
-            for (int k4 = 0; k4 < T2_WCH / 4; ++k4)
-              *reinterpret_cast<float4*>(dst + k4 * 32) =
-                  make_float4(rx[(4 * k4) * T2_LDS + et], rx[(4 * k4 + 1) * T2_LDS + et], rx[(4 * k4 + 2) * T2_LDS + et], rx[(4 * k4 + 3) * T2_LDS + et]);
-          } else {
-            for (int k4 = 0; k4 < T2_WCH / 4; ++k4) *reinterpret_cast<float4*>(dst + k4 * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        tc_fence_async_smem();
-        t2_arrive(&sh.full[2]);
-        t2_arrive(&sh.empty[s]);
       }
       if (nch > 0) {
+        if (et == 0) T2_STAMP(32);
         if (g.dbias && et < Mo) atomicAdd(g.dbias + et, bsum);
         const int o = q * 32 + lane;
         tc_mbar_wait(&sh.tfull[0], 0);
         tc_fence_after();
+        if (et == 0) T2_STAMP(33);
+        t2_ebar();                                      // every epilogue warp is done reading G tiles (bias gradient) before the stages are reused
+        // all MMAs have completed: the operand stages are free and become the staging tile [128][132], so that the split-K
+        // reduction goes out as row-contiguous vector reductions (one 512-byte row per warp instruction) instead of 32 lines per instruction
+        float* stg = t2_smem;
         for (int c0 = 0; c0 < nipad; c0 += 32) {
           float v[32];
           tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-          if (o < Mo) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              if (c0 + jj < Ni) atomicAdd(g.C + (int64_t)o * g.ldc + c0 + jj, v[jj]);
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(stg + (size_t)o * T2_LDS + c0 + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+        __syncwarp();                                   // warp q wrote rows q*32 .. q*32+31 and reduces exactly those rows
+        const bool v4 = (g.ldc & 3) == 0 && (Ni & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
+        for (int r = q * 32; r < min(q * 32 + 32, Mo); ++r) {
+          float* crow = g.C + (int64_t)r * g.ldc;
+          if (v4) {
+            if (4 * lane < Ni) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)r * T2_LDS + 4 * lane);
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * lane), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+            }
+          } else {
+            for (int n = lane; n < Ni; n += 32) atomicAdd(crow + n, stg[(size_t)r * T2_LDS + n]);
           }
         }
         tc_fence_before();
+        if (et == 0) T2_STAMP(34);
       }
     }
   }

@@ -10,7 +10,7 @@
 
 #include <stdlib.h>
 
-#include "gemm_tc2.cuh"
+#include "mlp_chain.cuh"
 
 namespace dwbc {
 
@@ -50,6 +50,7 @@ struct Plan {
   float* hc2;                     // [rows*3, 12]
   float* zh;                      // [rows, latent]
   float* hw1; float* hw2; float* hwl;      // re-packed weights
+  float* wpack;                            // packed weight images of the fused chain kernels (mlp_chain.cuh)
   // gradients
   float* g_leg; float* g_arm; float* g_vl; float* g_va; float* g_z;
   float* d0; float* d1; float* d2;         // ping-pong [rows, maxw]
@@ -90,6 +91,7 @@ static Plan make_plan(const DwbcNetCfg& n, int64_t rows, void* ws) {
   p.hc2 = b.f(rows * 3 * 12);
   p.zh = b.f(rows * align_up(p.latent, 4));
   p.hw1 = b.f(20 * 128); p.hw2 = b.f(10 * 40); p.hwl = b.f(32 * 36);
+  p.wpack = b.f((int64_t)CH_MAX_PACK * (CH_WBUF + 64));
   p.g_leg = b.f(rows * align_up(n.n_leg, 4)); p.g_arm = b.f(rows * align_up(n.n_arm, 4));
   p.g_vl = b.f(rows); p.g_va = b.f(rows); p.g_z = b.f(rows * align_up(p.latent, 4));
   p.d0 = b.f(rows * p.maxw); p.d1 = b.f(rows * p.maxw); p.d2 = b.f(rows * p.maxw);
@@ -262,6 +264,80 @@ static int critic_forward(const DwbcNetCfg& n, const float* P, const float* obs,
   }
   TRY(head_forward(P, h, in, n.n_leg_layers, n.leg_dims, 1, n.off_cleg_w, n.off_cleg_b, p.cl, value, 2, ACT_NONE, rows, st));
   TRY(head_forward(P, h, in, n.n_arm_layers, n.arm_dims, 1, n.off_carm_w, n.off_carm_b, p.ca, value + 1, 2, ACT_NONE, rows, st));
+  return DWBC_OK;
+}
+
+// ---- fused forward (TF32 path): priv encoder + actor in ONE launch, critic in one launch (mlp_chain.cuh) --------------
+static bool chain_usable(const DwbcNetCfg& n, const Plan& p, const float* obs, int64_t obs_stride) {
+  if (mlp_precision != 1 || tc_simple || getenv("DWBC_NO_CHAIN")) return false;
+  auto ok = [](const int32_t* d, int k) { for (int i = 0; i < k; ++i) if (d[i] > 128 || (d[i] & 3)) return false; return true; };
+  if (!ok(n.priv_dims, n.n_priv_layers) || !ok(n.actor_dims, n.n_actor_layers) || !ok(n.critic_dims, n.n_critic_layers) ||
+      !ok(n.leg_dims, n.n_leg_layers) || !ok(n.arm_dims, n.n_arm_layers))
+    return false;
+  if ((n.num_prop & 3) || (n.num_priv & 3) || (p.latent & 3) || n.num_prop + p.latent > 128 || n.num_prop + n.num_priv > 128 || n.num_priv > 128)
+    return false;
+  if ((obs_stride & 3) || !chain_aligned(obs)) return false;
+  if (n.n_priv_layers + n.n_actor_layers + n.n_leg_layers + n.n_arm_layers + 2 > CH_MAX_OPS) return false;
+  if (n.n_critic_layers + n.n_leg_layers + n.n_arm_layers + 2 > CH_MAX_OPS) return false;
+  return true;
+}
+
+static void chain_head(ChainBuilder& b, const float* P, int trunk_buf, int in, int nl, const int32_t* dims, int n_out, const int64_t* ow,
+                       const int64_t* ob, float* const* acts, bool store, float* out, int64_t ldo, int last_act) {
+  int a = trunk_buf;
+  for (int l = 0; l < nl; ++l) {          // hidden layers live in buffer 0 (the trunk stays intact in buffer 1 for the other head)
+    b.op(P + ow[l], in, P + ob[l], dims[l], in, ACT_ELU, a, 0, 0, store ? acts[l] : nullptr, dims[l]);
+    a = 0;
+    in = dims[l];
+  }
+  b.op(P + ow[nl], in, P + ob[nl], n_out, in, last_act, a, -1, 0, out, ldo);
+}
+
+// z_hist == nullptr: latent from the privileged encoder (computed inside the chain); else the history latent [rows, zld]
+static int forward_chains(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows,
+                          const float* z_hist, int zld, const Plan& p, float* value, bool store, bool actor, bool critic, cudaStream_t st) {
+  PackList pl{};
+  pl.out = p.wpack;
+  int64_t off = 0;
+  ChainBuilder A(&pl, &off, rows), C(&pl, &off, rows);
+  if (actor) {
+    const int in0 = n.num_prop + p.latent;
+    A.load(rowmat_gather(obs, idx, obs_stride), n.num_prop, 1, 0, z_hist ? n.num_prop : n.num_prop);
+    if (z_hist) {
+      A.load(rowmat(z_hist, zld), p.latent, 1, n.num_prop, (in0 + 7) & ~7);
+    } else {
+      A.load(rowmat_gather(obs + n.num_prop, idx, obs_stride), n.num_priv, 0, 0, (n.num_priv + 7) & ~7);
+      int in = n.num_priv;
+      for (int l = 0; l < n.n_priv_layers; ++l) {                                  // AC:219-221
+        const bool lastl = l == n.n_priv_layers - 1;
+        A.op(P + n.off_priv_w[l], in, P + n.off_priv_b[l], n.priv_dims[l], in, ACT_ELU, 0, lastl ? 1 : 0, lastl ? n.num_prop : 0,
+             store ? p.priv[l] : nullptr, align_up(n.priv_dims[l], 4));
+        in = n.priv_dims[l];
+      }
+    }
+    int in = in0;
+    for (int l = 0; l < n.n_actor_layers; ++l) {                                   // AC:211-213, input cat([obs_prop, z]) sits in buffer 1
+      A.op(P + n.off_actor_w[l], in, P + n.off_actor_b[l], n.actor_dims[l], in, ACT_ELU, 1, 1, 0, store ? p.ab[l] : nullptr, n.actor_dims[l]);
+      in = n.actor_dims[l];
+    }
+    chain_head(A, P, 1, in, n.n_leg_layers, n.leg_dims, n.n_leg, n.off_aleg_w, n.off_aleg_b, p.al, store, p.mean, p.mean_ld, ACT_TANH);
+    chain_head(A, P, 1, in, n.n_arm_layers, n.arm_dims, n.n_arm, n.off_aarm_w, n.off_aarm_b, p.aa, store, p.mean + n.n_leg, p.mean_ld, ACT_TANH);
+    if (!A.ok) return DWBC_ERR_UNSUPPORTED;
+  }
+  if (critic) {
+    int in = n.num_prop + n.num_priv;
+    C.load(rowmat_gather(obs, idx, obs_stride), in, 1, 0, (in + 7) & ~7);
+    for (int l = 0; l < n.n_critic_layers; ++l) {                                  // AC:280-286
+      C.op(P + n.off_critic_w[l], in, P + n.off_critic_b[l], n.critic_dims[l], in, ACT_ELU, 1, 1, 0, store ? p.cb[l] : nullptr, n.critic_dims[l]);
+      in = n.critic_dims[l];
+    }
+    chain_head(C, P, 1, in, n.n_leg_layers, n.leg_dims, 1, n.off_cleg_w, n.off_cleg_b, p.cl, store, value, 2, ACT_NONE);
+    chain_head(C, P, 1, in, n.n_arm_layers, n.arm_dims, 1, n.off_carm_w, n.off_carm_b, p.ca, store, value + 1, 2, ACT_NONE);
+    if (!C.ok) return DWBC_ERR_UNSUPPORTED;
+  }
+  TRY(launch_pack(pl, st));
+  if (actor) TRY(launch_chain(A.pr, st));
+  if (critic) TRY(launch_chain(C.pr, st));
   return DWBC_OK;
 }
 
@@ -473,15 +549,20 @@ extern "C" int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const
   Plan p = make_plan(n, rows, workspace);
   const float* z;
   int zld = (int)align_up(p.latent, 4);
-  if (hist_encoding) {
-    TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
-    z = p.zh;
+  if (chain_usable(n, p, obs, obs_stride)) {
+    if (hist_encoding) TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+    TRY(forward_chains(n, params, obs, nullptr, obs_stride, rows, hist_encoding ? p.zh : nullptr, zld, p, values, false, true, true, st));
   } else {
-    TRY(priv_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
-    z = p.priv[n.n_priv_layers - 1];
+    if (hist_encoding) {
+      TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+      z = p.zh;
+    } else {
+      TRY(priv_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+      z = p.priv[n.n_priv_layers - 1];
+    }
+    TRY(actor_forward(n, params, obs, nullptr, obs_stride, rows, z, zld, p, st));
+    TRY(critic_forward(n, params, obs, nullptr, obs_stride, rows, p, values, st));
   }
-  TRY(actor_forward(n, params, obs, nullptr, obs_stride, rows, z, zld, p, st));
-  TRY(critic_forward(n, params, obs, nullptr, obs_stride, rows, p, values, st));
   act_finalize_kernel<<<(rows + 127) / 128, 128, 0, st>>>(p.mean, p.mean_ld, params + n.off_std, eps, actions, log_prob, mean, sigma, rows,
                                                            n.n_leg, n.n_leg + n.n_arm);
   DWBC_LAUNCH_CHECK();
@@ -493,6 +574,8 @@ extern "C" int dwbc_critic_values(const DwbcNetCfg* net, const float* params, co
   TRY(check_net(net));
   if (!params || !obs || !values || !workspace || rows <= 0) return DWBC_ERR_ARG;
   Plan p = make_plan(*net, rows, workspace);
+  if (chain_usable(*net, p, obs, obs_stride))
+    return forward_chains(*net, params, obs, nullptr, obs_stride, rows, nullptr, 0, p, values, false, false, true, (cudaStream_t)stream);
   return critic_forward(*net, params, obs, nullptr, obs_stride, rows, p, values, (cudaStream_t)stream);
 }
 
@@ -512,11 +595,15 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
 
   // forward (the reference evaluates the actor 3x and the priv encoder 3x per mini-batch,
   // PPO:166,174,230; identical values, so each is evaluated once here)
-  TRY(priv_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));
-  TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));           // PPO:175-176 (no grad)
   float* z = p.priv[n.n_priv_layers - 1];
-  TRY(actor_forward(n, P, s->observations, idx, s->obs_stride, rows, z, Lld, p, st));
-  TRY(critic_forward(n, P, s->observations, idx, s->obs_stride, rows, p, p.value, st));
+  TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));           // PPO:175-176 (no grad)
+  if (chain_usable(n, p, s->observations, s->obs_stride)) {
+    TRY(forward_chains(n, P, s->observations, idx, s->obs_stride, rows, nullptr, Lld, p, p.value, true, true, true, st));
+  } else {
+    TRY(priv_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));
+    TRY(actor_forward(n, P, s->observations, idx, s->obs_stride, rows, z, Lld, p, st));
+    TRY(critic_forward(n, P, s->observations, idx, s->obs_stride, rows, p, p.value, st));
+  }
 
   LossArgs a{};
   a.mean = p.mean; a.mean_ld = p.mean_ld; a.std = P + n.off_std; a.value = p.value; a.zp = z; a.zld = Lld; a.zh = p.zh;

@@ -1,0 +1,312 @@
+// Fused layer chain on the tcgen05 tensor cores: a whole sub-network of the ActorCritic (AC:86-353) per launch.
+//
+// The layer-wise kernels (gemm_tc2.cuh) are bounded by operand fills and epilogue stores: every hidden activation makes a
+// round trip through L2/HBM between two layers.  Here one persistent CTA owns a 128-row tile and runs a small PROGRAM of
+// layer ops on it; activations stay in shared memory in the K-major operand layout of the next layer:
+//
+//   loads : gathered rows of the observation (mini-batch index, RS:189-201) -> operand tiles, cp.async, zero-filled tails
+//   op    : D[128 x N] (TMEM) = A tile[128 x K] (smem) * W^T ;  W comes pre-packed in the UMMA canonical layout
+//           (pack_weights_kernel, one tiny launch per call) and is fetched with ONE bulk async copy per op, bias appended;
+//           epilogue: TMEM -> registers -> bias + ELU / tanh -> (a) operand tile of the next op (same or other buffer, at
+//           a column offset: this is how cat([obs_prop, z]) of AC:211 is formed without a concat buffer), (b) optionally the
+//           global activation buffer the backward pass needs, written from the tile with 64-byte row segments.
+//
+// Warp roles (288 threads): warps 0-3 producers (tile loads), warp 4 one elected thread: weight bulk copies + tcgen05.mma
+// + tcgen05.commit, warps 5-8 epilogue (TMEM lane quarter = warp % 4).  All hand-offs are mbarriers; the ops of one tile
+// are strictly sequential (each needs the previous output), the weight copy of op i+1 overlaps the epilogue of op i and
+// the global stores of op i overlap the MMAs of op i+1.
+//
+// Tiles use ONE geometry: [128 rows x 128 k] fp32, element (r, k) at float ((r/8)*32 + k/4)*32 + (r%8)*4 + k%4
+// (8-row x 16-byte core matrices, LBO = 128 B, SBO = 4096 B); an op reads k < kpad only.
+#pragma once
+#include "gemm_tc2.cuh"
+
+namespace dwbc {
+
+constexpr int CH_MAX_OPS = 12, CH_MAX_LOADS = 3, CH_MAX_PACK = 24;
+constexpr int CH_TILE = 128 * 128;                 // floats per operand tile
+constexpr int CH_WBUF = 128 * 128 + 2 * 128;       // packed weight image + two bias slots (op parity)
+
+struct ChainLoad {
+  RowMat src;        // rows of the source (already offset to the first column)
+  int ncols;         // columns copied (multiple of 4)
+  int buf, col0;     // destination tile and column (multiple of 4)
+  int zero_to;       // columns [col0 + ncols, zero_to) are zero-filled (K padding of the consuming op)
+};
+struct ChainOp {
+  const float* wp;   // packed image: canonical K-major [npad x kpad] weights, then [npad] bias
+  float* y;          // global output (nullable), row-major
+  int64_t ldy;
+  int a_buf, kpad;   // input tile, padded reduction length (multiple of 8)
+  int N, npad;       // outputs (npad: multiple of 16)
+  int act;
+  int out_buf, out_col0;   // next operand tile (-1: none) and column offset (multiple of 4)
+};
+struct ChainProg {
+  int M, n_loads, n_ops;
+  ChainLoad ld[CH_MAX_LOADS];
+  ChainOp op[CH_MAX_OPS];
+};
+
+struct PackItem { const float* w; int64_t ldw; const float* bias; int N, K, npad, kpad; int64_t dst; };
+struct PackList { int n; float* out; PackItem it[CH_MAX_PACK]; };
+
+// weights [N x K] (row stride ldw) -> canonical K-major image [npad x kpad] (+ bias[npad]); pads are zero
+__global__ void pack_weights_kernel(const PackList pl) {
+  const PackItem& it = pl.it[blockIdx.y];
+  const int wn = it.npad * it.kpad, total = wn + it.npad;
+  float* dst = pl.out + it.dst;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < wn) {
+      const int n = i / it.kpad, k = i - n * it.kpad;
+      const float v = (n < it.N && k < it.K) ? it.w[(int64_t)n * it.ldw + k] : 0.0f;
+      dst[((size_t)((n >> 3) * (it.kpad >> 2) + (k >> 2)) * 8 + (n & 7)) * 4 + (k & 3)] = v;
+    } else {
+      const int n = i - wn;
+      dst[i] = (it.bias && n < it.N) ? it.bias[n] : 0.0f;
+    }
+  }
+}
+
+struct ChShared {
+  uint64_t w_full, ld_full, mma_done, epi_done, tile_done;
+  uint32_t tmem_base;
+  int64_t rowoff[CH_MAX_LOADS][128];
+};
+
+__device__ __forceinline__ void ch_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ch_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(dst_smem)), "l"(src),
+               "r"(bytes), "r"(tc_smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_constant__ ChainProg pr, const int tiles) {
+  extern __shared__ __align__(1024) float ch_smem[];
+  __shared__ ChShared sh;
+  float* buf[2] = {ch_smem, ch_smem + CH_TILE};
+  float* wbuf = ch_smem + 2 * CH_TILE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    tc_mbar_init(&sh.w_full, 1);
+    tc_mbar_init(&sh.ld_full, T2_PROD);
+    tc_mbar_init(&sh.mma_done, 1);
+    tc_mbar_init(&sh.epi_done, T2_EPI);
+    tc_mbar_init(&sh.tile_done, T2_EPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tc_tmem_alloc(&sh.tmem_base, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+  const int my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nops = pr.n_ops;
+
+  if (warp < 4) {
+    // ===================== PRODUCERS: tile loads =====================
+    const int ptid = tid;
+    for (int j = 0; j < my_tiles; ++j) {
+      const int64_t m0 = (int64_t)(blockIdx.x + j * gridDim.x) * TC_M;
+      const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
+      t2_pbar();                                             // row-offset table of the previous tile no longer read
+      for (int l = 0; l < pr.n_loads; ++l)
+        sh.rowoff[l][ptid] = ptid < rows ? (pr.ld[l].src.row(m0 + ptid) - pr.ld[l].src.p) : 0;
+      if (j > 0) tc_mbar_wait(&sh.tile_done, (j - 1) & 1);   // every MMA and every tile read of the previous tile has retired
+      t2_pbar();
+      for (int l = 0; l < pr.n_loads; ++l) {
+        const ChainLoad& L = pr.ld[l];
+        const int cpr = L.ncols >> 2, c40 = L.col0 >> 2;
+        const uint32_t d0 = tc_smem_u32(buf[L.buf]);
+        const float* base = L.src.p;
+        const int64_t* ro = sh.rowoff[l];
+        const int total = TC_M * cpr;
+        const int z0 = (L.col0 + L.ncols) >> 2, nz = (L.zero_to >> 2) - z0;      // zero pieces per row (K padding), written first
+        for (int i = ptid; i < TC_M * nz; i += T2_PROD) {
+          const int r = i / nz, c = i - r * nz;
+          *reinterpret_cast<float4*>(buf[L.buf] + ((size_t)((r >> 3) * 32 + z0 + c) * 8 + (r & 7)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int i = ptid; i < total; i += T2_PROD) {
+          const int r8 = i & 7, rest = i >> 3;
+          const int g = rest / cpr, c = rest - g * cpr;
+          const int r = g * 8 + r8;
+          const float* src = r < rows ? base + ro[r] + 4 * c : base;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + (uint32_t)(((g * 32 + c40 + c) * 8 + r8) * 16)), "l"(src),
+                       "r"(r < rows ? 16 : 0)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.ld_full)) : "memory");
+    }
+  } else if (warp == 4) {
+    // ===================== weight copies + MMA issue (one thread) =====================
+    if (lane == 0 && my_tiles > 0) {
+      // weights of op (global index n) -> wbuf, its bias -> bias slot n & 1: the epilogue of op n still reads its bias while
+      // the weights of op n+1 stream in
+      auto fetch_w = [&](int i, uint32_t nn) {
+        const uint32_t wbytes = (uint32_t)(pr.op[i].npad * pr.op[i].kpad) * 4u, bbytes = (uint32_t)pr.op[i].npad * 4u;
+        ch_expect_tx(&sh.w_full, wbytes + bbytes);
+        ch_bulk_g2s(wbuf, pr.op[i].wp, wbytes, &sh.w_full);
+        ch_bulk_g2s(wbuf + CH_TILE + (nn & 1) * 128, pr.op[i].wp + pr.op[i].npad * pr.op[i].kpad, bbytes, &sh.w_full);
+      };
+      fetch_w(0, 0);
+      uint32_t n = 0;
+      const uint32_t b0 = tc_smem_u32(wbuf);
+      for (int j = 0; j < my_tiles; ++j) {
+        for (int i = 0; i < nops; ++i, ++n) {
+          const ChainOp& o = pr.op[i];
+          tc_mbar_wait(&sh.w_full, n & 1);
+          if (i == 0) tc_mbar_wait(&sh.ld_full, j & 1);
+          if (n > 0) tc_mbar_wait(&sh.epi_done, (n - 1) & 1);   // previous epilogue: accumulator drained, its output tile written
+          tc_fence_async_smem();                                // generic-proxy tile writes (cp.async, epilogue stores) -> async-proxy MMA reads
+          tc_fence_after();
+          const uint32_t idesc = tc_idesc(o.npad, false, false);
+          const uint32_t a0 = tc_smem_u32(buf[o.a_buf]);
+          for (int kk = 0; kk < o.kpad; kk += 8) {
+            const uint64_t ad = tc_desc(a0 + (kk >> 2) * 128, 128, 4096);
+            const uint64_t bd = tc_desc(b0 + (kk >> 2) * 128, 128, (o.kpad >> 2) * 128);
+            tc_mma_tf32(tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
+          }
+          tc_commit(&sh.mma_done);
+          tc_mbar_wait(&sh.mma_done, n & 1);                    // weights consumed: the buffer may be refilled while the epilogue runs
+          if (i + 1 < nops) fetch_w(i + 1, n + 1);
+          else if (j + 1 < my_tiles) fetch_w(0, n + 1);
+        }
+      }
+    }
+  } else {
+    // ===================== EPILOGUE =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // tile row of this thread
+    uint32_t n = 0;
+    for (int j = 0; j < my_tiles; ++j) {
+      const int64_t m0 = (int64_t)(blockIdx.x + j * gridDim.x) * TC_M;
+      const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
+      for (int i = 0; i < nops; ++i, ++n) {
+        const ChainOp& o = pr.op[i];
+        tc_mbar_wait(&sh.mma_done, n & 1);
+        tc_fence_after();
+        const float* bias = wbuf + CH_TILE + (n & 1) * 128;
+        float* otile = o.out_buf >= 0 ? buf[o.out_buf] + ((size_t)((r >> 3) * 32 + (o.out_col0 >> 2)) * 8 + (r & 7)) * 4 : nullptr;
+        const bool direct = o.y != nullptr && o.out_buf < 0;
+        float* yrow = o.y ? o.y + (m0 + r) * o.ldy : nullptr;
+        const bool yv4 = direct && (o.ldy & 3) == 0 && (o.N & 3) == 0 && (reinterpret_cast<uintptr_t>(o.y) & 15) == 0;
+        for (int c0 = 0; c0 < o.npad; c0 += 32) {
+          float v[32];
+          tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            float x = v[jj] + bias[c0 + jj];      // columns >= N are discarded below (stale pad values never propagate)
+            if (o.act == ACT_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;
+            else if (o.act == ACT_TANH) x = tanhf(x);
+            v[jj] = (c0 + jj < o.N) ? x : 0.0f;
+          }
+          if (otile) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(otile + (size_t)((c0 >> 2) + j4) * 32) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+          if (direct && r < rows) {
+            if (yv4) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                if (c0 + 4 * j4 < o.N) *reinterpret_cast<float4*>(yrow + c0 + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj)
+                if (c0 + jj < o.N) yrow[c0 + jj] = v[jj];
+            }
+          }
+        }
+        tc_fence_before();
+        if (otile) tc_fence_async_smem();
+        t2_arrive(&sh.epi_done);
+        if (o.y != nullptr && o.out_buf >= 0) {
+          // global copy of this warp's 32 rows out of the tile it just wrote: 8 rows x 64 contiguous bytes per instruction
+          __syncwarp();
+          const int r8 = lane & 7, pp = lane >> 3, np4 = o.N >> 2;
+          const float* t0 = buf[o.out_buf];
+          if ((o.N & 3) == 0 && (o.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(o.y) & 15) == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int rr = q * 32 + g * 8 + r8;
+              if (rr >= rows) continue;
+              const float* trow = t0 + ((size_t)((rr >> 3) * 32 + (o.out_col0 >> 2)) * 8 + r8) * 4;
+              float* yr = o.y + (m0 + rr) * o.ldy;
+              for (int p0 = 0; p0 < np4; p0 += 4) {
+                const int piece = p0 + pp;
+                if (piece < np4) *reinterpret_cast<float4*>(yr + 4 * piece) = *reinterpret_cast<const float4*>(trow + (size_t)piece * 32);
+              }
+            }
+          } else if (r < rows) {
+            const float* trow = t0 + ((size_t)((r >> 3) * 32 + (o.out_col0 >> 2)) * 8 + (r & 7)) * 4;
+            for (int c = 0; c < o.N; ++c) yrow[c] = trow[(size_t)(c >> 2) * 32 + (c & 3)];
+          }
+        }
+      }
+      t2_arrive(&sh.tile_done);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) tc_tmem_dealloc(tmem, 128);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+inline bool chain_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline int launch_pack(const PackList& pl, cudaStream_t st) {
+  if (pl.n <= 0) return DWBC_OK;
+  pack_weights_kernel<<<dim3(8, pl.n), 256, 0, st>>>(pl);
+  ++dwbc_launch_counter;
+  return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
+}
+
+inline int launch_chain(const ChainProg& pr, cudaStream_t st) {
+  if (pr.M <= 0 || pr.n_ops <= 0 || pr.n_ops > CH_MAX_OPS || pr.n_loads < 0 || pr.n_loads > CH_MAX_LOADS) return DWBC_ERR_ARG;
+  if (pr.op[pr.n_ops - 1].out_buf >= 0) return DWBC_ERR_ARG;      // the last op must not write a tile (next tile's loads start behind it)
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = (pr.M + TC_M - 1) / TC_M;
+  const int grid = tiles < sms ? tiles : sms;
+  const size_t smem = (size_t)(2 * CH_TILE + CH_WBUF) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DWBC_ERR_LAUNCH;
+    attr = true;
+  }
+  chain_fwd_kernel<<<grid, T2_THREADS, smem, st>>>(pr, tiles);
+  ++dwbc_launch_counter;
+  return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
+}
+
+// Small builder: keeps the pack list and the program in step.
+struct ChainBuilder {
+  ChainProg pr{};
+  PackList* pl;
+  int64_t* pack_off;       // running float offset into the packed-weight buffer
+  bool ok = true;
+  ChainBuilder(PackList* pl_, int64_t* off, int M) : pl(pl_), pack_off(off) { pr.M = M; }
+  void load(RowMat src, int ncols, int buf, int col0, int zero_to) {
+    if (pr.n_loads >= CH_MAX_LOADS || (ncols & 3) || (col0 & 3) || (zero_to & 3) || zero_to < col0 + ncols || zero_to > 128 ||
+        !chain_aligned(src.p) || (src.stride_g & 3) || (src.ld & 3)) { ok = false; return; }
+    pr.ld[pr.n_loads++] = ChainLoad{src, ncols, buf, col0, zero_to};
+  }
+  // y = act(A[:, :K] W^T + b);  W [N x K] row-major with row stride ldw
+  void op(const float* W, int64_t ldw, const float* bias, int N, int K, int act, int a_buf, int out_buf, int out_col0, float* y, int64_t ldy) {
+    const int npad = (N + 15) & ~15, kpad = (K + 7) & ~7;
+    if (pr.n_ops >= CH_MAX_OPS || pl->n >= CH_MAX_PACK || N > 128 || K > 128 || (out_col0 & 3) || (out_buf >= 0 && out_col0 + ((npad + 31) & ~31) > 128)) { ok = false; return; }
+    PackItem& it = pl->it[pl->n++];
+    it = PackItem{W, ldw, bias, N, K, npad, kpad, *pack_off};
+    pr.op[pr.n_ops++] = ChainOp{pl->out ? pl->out + *pack_off : nullptr, y, ldy, a_buf, kpad, N, npad, act, out_buf, out_col0};
+    *pack_off += (int64_t)npad * kpad + npad;
+    *pack_off = (*pack_off + 63) & ~(int64_t)63;      // 256-byte aligned images (bulk copies need 16)
+  }
+};
+
+}  // namespace dwbc

@@ -259,3 +259,28 @@ def test_tf32_tensor_core_path_matches_reference_within_stated_tolerance():
     p20 = torch.cat([v.reshape(-1) for v in _flat_ref(ac, g["param20"]).values()])
     gotp = torch.cat([v.reshape(-1).cpu() for v in ac.unflat(ac.flat).values()])
     assert float((gotp - p20).abs().max()) < 4e-3
+
+
+@pytest.mark.parametrize("hist", [False, True])
+def test_fused_chain_forward_matches_fp32_path_many_tiles(hist):
+    """The fused layer-chain kernel (TF32, mlp_chain.cuh) against the exact-fp32 layer-wise path of the same library
+    (itself pinned to the reference by the tests above) at a row count that gives every CTA several tiles plus a ragged
+    last tile.  Stated tolerance: 2e-2 abs on means / values (TF32 inputs through up to 6 layers)."""
+    g = np.load(os.path.join(G, "ppo.npz"))
+    P = golden_params(g, int(g["meta"][2]))
+    N = 148 * 128 * 2 + 3 * 128 + 77
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.randn(N, 860, device="cuda", generator=gen)
+    eps = torch.randn(N, 18, device="cuda", generator=gen)
+    out = {}
+    for prec in ("fp32", "tf32"):
+        alg = make_alg(N, 1, P, precision=prec)
+        alg.act(obs, obs, hist, eps=eps)
+        s = alg.storage
+        alg.compute_returns(obs)                                   # critic-only chain (PPO:148-150)
+        out[prec] = [s.mu[0].clone(), s.values[0].clone(), s.actions[0].clone(), s.actions_log_prob[0].clone(), alg._last_values.clone()]
+        del alg
+    for a, b in zip(out["fp32"][:3] + out["fp32"][4:], out["tf32"][:3] + out["tf32"][4:]):
+        assert float((a - b).abs().max()) < 2e-2
+    assert float((out["fp32"][3] - out["tf32"][3]).abs().max()) < 1e-3      # log-prob of a = mu + sigma*eps does not depend on mu
+    assert torch.isfinite(out["tf32"][0]).all() and torch.isfinite(out["tf32"][1]).all()

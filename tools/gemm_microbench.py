@@ -29,7 +29,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "stamps":
     buf = torch.zeros(148 * 64, dtype=torch.int64, device="cuda")
     lib.dwbc_debug_set_tc_cycle_buffer.argtypes = [C.c_void_p]
     lib.dwbc_debug_set_tc_cycle_buffer(buf.data_ptr())
-    run(0, 1, 0); torch.cuda.synchronize()
+    run(int(sys.argv[2]) if len(sys.argv) > 2 else 0, 1, 0); torch.cuda.synchronize()
     c = buf.view(148, 64).cpu()
     for b in (0, 1, 147):
         row = c[b]; t0 = int(row[0])
