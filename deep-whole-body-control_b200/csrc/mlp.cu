@@ -551,7 +551,7 @@ extern "C" int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const
   int zld = (int)align_up(p.latent, 4);
   if (chain_usable(n, p, obs, obs_stride)) {
     if (hist_encoding) TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
-    TRY(forward_chains(n, params, obs, nullptr, obs_stride, rows, hist_encoding ? p.zh : nullptr, zld, p, values, false, true, true, st));
+    TRY(forward_chains(n, params, obs, nullptr, obs_stride, rows, hist_encoding ? p.zh : nullptr, zld, p, values, getenv("DWBC_CHAIN_STORE") != nullptr /* profiling aid */, true, true, st));
   } else {
     if (hist_encoding) {
       TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));

@@ -11,8 +11,8 @@
 //           a column offset: this is how cat([obs_prop, z]) of AC:211 is formed without a concat buffer), (b) optionally the
 //           global activation buffer the backward pass needs, written from the tile with 64-byte row segments.
 //
-// Warp roles (288 threads): warps 0-3 producers (tile loads), warp 4 one elected thread: weight bulk copies + tcgen05.mma
-// + tcgen05.commit, warps 5-8 epilogue (TMEM lane quarter = warp % 4).  All hand-offs are mbarriers; the ops of one tile
+// Warp roles (288 threads): warps 0-3 tile loads, warp 4 one elected thread: weight bulk copies + tcgen05.mma
+// + tcgen05.commit, warps 0-3 and 5-8 epilogue (TMEM lane quarter = warp % 4, the two warps of a quarter split the columns).  All hand-offs are mbarriers; the ops of one tile
 // are strictly sequential (each needs the previous output), the weight copy of op i+1 overlaps the epilogue of op i and
 // the global stores of op i overlap the MMAs of op i+1.
 //
@@ -83,6 +83,20 @@ __device__ __forceinline__ void ch_bulk_g2s(void* dst_smem, const void* src, uin
                : "memory");
 }
 
+template <int kAct>
+__device__ __forceinline__ void ch_bias_act(float* v, const float* bias, int nvalid) {
+  if (kAct == ACT_TANH) {                 // narrow output heads only: skip the columns beyond N
+    for (int jj = 0; jj < 32; ++jj) v[jj] = jj < nvalid ? t2_tanh(v[jj] + bias[jj]) : 0.0f;
+    return;
+  }
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) {
+    float x = v[jj] + bias[jj];
+    if (kAct == ACT_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;
+    v[jj] = jj < nvalid ? x : 0.0f;
+  }
+}
+
 __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_constant__ ChainProg pr, const int tiles) {
   extern __shared__ __align__(1024) float ch_smem[];
   __shared__ ChShared sh;
@@ -93,7 +107,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
     tc_mbar_init(&sh.w_full, 1);
     tc_mbar_init(&sh.ld_full, T2_PROD);
     tc_mbar_init(&sh.mma_done, 1);
-    tc_mbar_init(&sh.epi_done, T2_EPI);
+    tc_mbar_init(&sh.epi_done, T2_PROD + T2_EPI);
     tc_mbar_init(&sh.tile_done, T2_EPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -102,45 +116,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+  if (tid == 0) T2_STAMP(62);
   const int my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int nops = pr.n_ops;
 
-  if (warp < 4) {
-    // ===================== PRODUCERS: tile loads =====================
-    const int ptid = tid;
-    for (int j = 0; j < my_tiles; ++j) {
-      const int64_t m0 = (int64_t)(blockIdx.x + j * gridDim.x) * TC_M;
-      const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
-      t2_pbar();                                             // row-offset table of the previous tile no longer read
-      for (int l = 0; l < pr.n_loads; ++l)
-        sh.rowoff[l][ptid] = ptid < rows ? (pr.ld[l].src.row(m0 + ptid) - pr.ld[l].src.p) : 0;
-      if (j > 0) tc_mbar_wait(&sh.tile_done, (j - 1) & 1);   // every MMA and every tile read of the previous tile has retired
-      t2_pbar();
-      for (int l = 0; l < pr.n_loads; ++l) {
-        const ChainLoad& L = pr.ld[l];
-        const int cpr = L.ncols >> 2, c40 = L.col0 >> 2;
-        const uint32_t d0 = tc_smem_u32(buf[L.buf]);
-        const float* base = L.src.p;
-        const int64_t* ro = sh.rowoff[l];
-        const int total = TC_M * cpr;
-        const int z0 = (L.col0 + L.ncols) >> 2, nz = (L.zero_to >> 2) - z0;      // zero pieces per row (K padding), written first
-        for (int i = ptid; i < TC_M * nz; i += T2_PROD) {
-          const int r = i / nz, c = i - r * nz;
-          *reinterpret_cast<float4*>(buf[L.buf] + ((size_t)((r >> 3) * 32 + z0 + c) * 8 + (r & 7)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int i = ptid; i < total; i += T2_PROD) {
-          const int r8 = i & 7, rest = i >> 3;
-          const int g = rest / cpr, c = rest - g * cpr;
-          const int r = g * 8 + r8;
-          const float* src = r < rows ? base + ro[r] + 4 * c : base;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + (uint32_t)(((g * 32 + c40 + c) * 8 + r8) * 16)), "l"(src),
-                       "r"(r < rows ? 16 : 0)
-                       : "memory");
-        }
-      }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.ld_full)) : "memory");
-    }
-  } else if (warp == 4) {
+  if (warp == 4) {
     // ===================== weight copies + MMA issue (one thread) =====================
     if (lane == 0 && my_tiles > 0) {
       // weights of op (global index n) -> wbuf, its bias -> bias slot n & 1: the epilogue of op n still reads its bias while
@@ -158,8 +138,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
         for (int i = 0; i < nops; ++i, ++n) {
           const ChainOp& o = pr.op[i];
           tc_mbar_wait(&sh.w_full, n & 1);
+          if (n < 10) T2_STAMP(6 * n + 0);
           if (i == 0) tc_mbar_wait(&sh.ld_full, j & 1);
           if (n > 0) tc_mbar_wait(&sh.epi_done, (n - 1) & 1);   // previous epilogue: accumulator drained, its output tile written
+          if (n < 10) T2_STAMP(6 * n + 1);
           tc_fence_async_smem();                                // generic-proxy tile writes (cp.async, epilogue stores) -> async-proxy MMA reads
           tc_fence_after();
           const uint32_t idesc = tc_idesc(o.npad, false, false);
@@ -171,19 +153,55 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
           }
           tc_commit(&sh.mma_done);
           tc_mbar_wait(&sh.mma_done, n & 1);                    // weights consumed: the buffer may be refilled while the epilogue runs
+          if (n < 10) T2_STAMP(6 * n + 2);
           if (i + 1 < nops) fetch_w(i + 1, n + 1);
           else if (j + 1 < my_tiles) fetch_w(0, n + 1);
         }
       }
     }
   } else {
-    // ===================== EPILOGUE =====================
+    // ===================== LOADS (warps 0-3) + EPILOGUE (warps 0-3 and 5-8) =====================
+    // Two warps share each TMEM lane quarter (warp % 4) and split an op's 32-column chunks: group 0 (warps 5-8) takes the
+    // even chunks, group 1 (warps 0-3, idle between two tile loads otherwise) the odd ones.  A warp copies to global memory
+    // exactly the chunks it wrote itself (128 contiguous bytes per row), so no cross-warp synchronisation is needed.
+    const int h = warp < 4 ? 1 : 0;
+    const int ptid = tid;                   // producer thread index (group 1 only)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // tile row of this thread
     uint32_t n = 0;
     for (int j = 0; j < my_tiles; ++j) {
       const int64_t m0 = (int64_t)(blockIdx.x + j * gridDim.x) * TC_M;
       const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
+      if (h == 1) {
+        t2_pbar();                                             // row-offset table of the previous tile no longer read
+        for (int l = 0; l < pr.n_loads; ++l)
+          sh.rowoff[l][ptid] = ptid < rows ? (pr.ld[l].src.row(m0 + ptid) - pr.ld[l].src.p) : 0;
+        if (j > 0) tc_mbar_wait(&sh.tile_done, (j - 1) & 1);   // group 0 has finished the previous tile too (all MMAs retired before that)
+        t2_pbar();
+        for (int l = 0; l < pr.n_loads; ++l) {
+          const ChainLoad& L = pr.ld[l];
+          const int cpr = L.ncols >> 2, c40 = L.col0 >> 2;
+          const uint32_t d0 = tc_smem_u32(buf[L.buf]);
+          const float* base = L.src.p;
+          const int64_t* ro = sh.rowoff[l];
+          const int total = TC_M * cpr;
+          const int z0 = (L.col0 + L.ncols) >> 2, nz = (L.zero_to >> 2) - z0;      // zero pieces per row (K padding), written first
+          for (int i = ptid; i < TC_M * nz; i += T2_PROD) {
+            const int rr = i / nz, cz = i - rr * nz;
+            *reinterpret_cast<float4*>(buf[L.buf] + ((size_t)((rr >> 3) * 32 + z0 + cz) * 8 + (rr & 7)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          for (int i = ptid; i < total; i += T2_PROD) {
+            const int r8 = i & 7, rest = i >> 3;
+            const int g = rest / cpr, cc = rest - g * cpr;
+            const int rr = g * 8 + r8;
+            const float* src = rr < rows ? base + ro[rr] + 4 * cc : base;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + (uint32_t)(((g * 32 + c40 + cc) * 8 + r8) * 16)), "l"(src),
+                         "r"(rr < rows ? 16 : 0)
+                         : "memory");
+          }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.ld_full)) : "memory");
+      }
       for (int i = 0; i < nops; ++i, ++n) {
         const ChainOp& o = pr.op[i];
         tc_mbar_wait(&sh.mma_done, n & 1);
@@ -192,24 +210,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
         float* otile = o.out_buf >= 0 ? buf[o.out_buf] + ((size_t)((r >> 3) * 32 + (o.out_col0 >> 2)) * 8 + (r & 7)) * 4 : nullptr;
         const bool direct = o.y != nullptr && o.out_buf < 0;
         float* yrow = o.y ? o.y + (m0 + r) * o.ldy : nullptr;
-        const bool yv4 = direct && (o.ldy & 3) == 0 && (o.N & 3) == 0 && (reinterpret_cast<uintptr_t>(o.y) & 15) == 0;
-        for (int c0 = 0; c0 < o.npad; c0 += 32) {
+        const bool yal = (o.ldy & 3) == 0 && (o.N & 3) == 0 && (reinterpret_cast<uintptr_t>(o.y) & 15) == 0;
+        for (int c0 = 32 * h; c0 < o.npad; c0 += 64) {
           float v[32];
           tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            float x = v[jj] + bias[c0 + jj];      // columns >= N are discarded below (stale pad values never propagate)
-            if (o.act == ACT_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;
-            else if (o.act == ACT_TANH) x = tanhf(x);
-            v[jj] = (c0 + jj < o.N) ? x : 0.0f;
-          }
+          // the activation is selected by a warp-uniform branch OUTSIDE the element loop (an if-converted tanh would be
+          // issued for every ELU element otherwise); columns >= N are forced to zero (stale pad values never propagate)
+          if (o.act == ACT_ELU) ch_bias_act<ACT_ELU>(v, bias + c0, o.N - c0);
+          else if (o.act == ACT_TANH) ch_bias_act<ACT_TANH>(v, bias + c0, o.N - c0);
+          else ch_bias_act<ACT_NONE>(v, bias + c0, o.N - c0);
           if (otile) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)
               *reinterpret_cast<float4*>(otile + (size_t)((c0 >> 2) + j4) * 32) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
           }
           if (direct && r < rows) {
-            if (yv4) {
+            if (yal) {
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4)
                 if (c0 + 4 * j4 < o.N) *reinterpret_cast<float4*>(yrow + c0 + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
@@ -222,34 +238,40 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
         }
         tc_fence_before();
         if (otile) tc_fence_async_smem();
+        if (tid == 160 && n < 10) T2_STAMP(6 * n + 3);
         t2_arrive(&sh.epi_done);
         if (o.y != nullptr && o.out_buf >= 0) {
-          // global copy of this warp's 32 rows out of the tile it just wrote: 8 rows x 64 contiguous bytes per instruction
+          // global copy of the chunks this warp just wrote, out of the tile: 8 rows x 64 contiguous bytes per instruction
           __syncwarp();
-          const int r8 = lane & 7, pp = lane >> 3, np4 = o.N >> 2;
+          const int r8 = lane & 7, pp = lane >> 3;
           const float* t0 = buf[o.out_buf];
-          if ((o.N & 3) == 0 && (o.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(o.y) & 15) == 0) {
+          for (int c0 = 32 * h; c0 < o.N; c0 += 64) {
+            if (yal) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int rr = q * 32 + g * 8 + r8;
-              if (rr >= rows) continue;
-              const float* trow = t0 + ((size_t)((rr >> 3) * 32 + (o.out_col0 >> 2)) * 8 + r8) * 4;
-              float* yr = o.y + (m0 + rr) * o.ldy;
-              for (int p0 = 0; p0 < np4; p0 += 4) {
-                const int piece = p0 + pp;
-                if (piece < np4) *reinterpret_cast<float4*>(yr + 4 * piece) = *reinterpret_cast<const float4*>(trow + (size_t)piece * 32);
+              for (int g = 0; g < 4; ++g) {
+                const int rr = q * 32 + g * 8 + r8;
+                if (rr >= rows) continue;
+                const float* trow = t0 + ((size_t)((rr >> 3) * 32 + ((o.out_col0 + c0) >> 2)) * 8 + r8) * 4;
+                float* yr = o.y + (m0 + rr) * o.ldy + c0;
+#pragma unroll
+                for (int p0 = 0; p0 < 8; p0 += 4) {
+                  const int piece = p0 + pp;
+                  if (c0 + 4 * piece < o.N) *reinterpret_cast<float4*>(yr + 4 * piece) = *reinterpret_cast<const float4*>(trow + (size_t)piece * 32);
+                }
               }
+            } else if (r < rows) {
+              const float* trow = t0 + ((size_t)((r >> 3) * 32 + ((o.out_col0 + c0) >> 2)) * 8 + (r & 7)) * 4;
+              for (int cc = 0; cc < 32 && c0 + cc < o.N; ++cc) yrow[c0 + cc] = trow[(size_t)(cc >> 2) * 32 + (cc & 3)];
             }
-          } else if (r < rows) {
-            const float* trow = t0 + ((size_t)((r >> 3) * 32 + (o.out_col0 >> 2)) * 8 + (r & 7)) * 4;
-            for (int c = 0; c < o.N; ++c) yrow[c] = trow[(size_t)(c >> 2) * 32 + (c & 3)];
           }
         }
+        if (tid == 160 && n < 10) T2_STAMP(6 * n + 4);
       }
-      t2_arrive(&sh.tile_done);
+      if (h == 0) t2_arrive(&sh.tile_done);
     }
   }
   __syncthreads();
+  if (tid == 0) T2_STAMP(63);
   if (warp == 4) tc_tmem_dealloc(tmem, 128);
 }
 
