@@ -52,7 +52,10 @@ struct Plan {
   float* hw1; float* hw2; float* hwl;      // re-packed weights
   float* wpack;                            // packed weight images of the fused chain kernels (mlp_chain.cuh)
   // gradients
-  float* g_leg; float* g_arm; float* g_vl; float* g_va; float* g_z;
+  float* g_leg; float* g_arm; float* g_vl; float* g_va; float* g_z;   // g_vl / g_va: columns 0 / 1 of one [rows, 4] buffer
+  // per-layer pre-activation gradients kept by the fused backward chain for the weight-gradient GEMMs
+  float* dza_l[DWBC_MAX_LAYERS]; float* dza_a[DWBC_MAX_LAYERS]; float* dza_b[DWBC_MAX_LAYERS]; float* dzp[DWBC_MAX_LAYERS];
+  float* dzc_l[DWBC_MAX_LAYERS]; float* dzc_a[DWBC_MAX_LAYERS]; float* dzc_b[DWBC_MAX_LAYERS];
   float* d0; float* d1; float* d2;         // ping-pong [rows, maxw]
   float* dz;                               // [rows, latent]
   float* dzh;                              // [rows, latent] (dagger)
@@ -91,9 +94,14 @@ static Plan make_plan(const DwbcNetCfg& n, int64_t rows, void* ws) {
   p.hc2 = b.f(rows * 3 * 12);
   p.zh = b.f(rows * align_up(p.latent, 4));
   p.hw1 = b.f(20 * 128); p.hw2 = b.f(10 * 40); p.hwl = b.f(32 * 36);
-  p.wpack = b.f((int64_t)CH_MAX_PACK * (CH_WBUF + 64));
+  p.wpack = b.f((int64_t)2 * CH_MAX_PACK * (CH_WBUF + 64));
   p.g_leg = b.f(rows * align_up(n.n_leg, 4)); p.g_arm = b.f(rows * align_up(n.n_arm, 4));
-  p.g_vl = b.f(rows); p.g_va = b.f(rows); p.g_z = b.f(rows * align_up(p.latent, 4));
+  p.g_vl = b.f(rows * 4); p.g_va = p.g_vl ? p.g_vl + 1 : nullptr; p.g_z = b.f(rows * align_up(p.latent, 4));
+  for (int i = 0; i < n.n_leg_layers; ++i) { p.dza_l[i] = b.f(rows * n.leg_dims[i]); p.dzc_l[i] = b.f(rows * n.leg_dims[i]); }
+  for (int i = 0; i < n.n_arm_layers; ++i) { p.dza_a[i] = b.f(rows * n.arm_dims[i]); p.dzc_a[i] = b.f(rows * n.arm_dims[i]); }
+  for (int i = 0; i < n.n_actor_layers; ++i) p.dza_b[i] = b.f(rows * n.actor_dims[i]);
+  for (int i = 0; i < n.n_critic_layers; ++i) p.dzc_b[i] = b.f(rows * n.critic_dims[i]);
+  for (int i = 0; i < n.n_priv_layers; ++i) p.dzp[i] = b.f(rows * align_up(n.priv_dims[i], 4));
   p.d0 = b.f(rows * p.maxw); p.d1 = b.f(rows * p.maxw); p.d2 = b.f(rows * p.maxw);
   p.dz = b.f(rows * align_up(p.latent, 4));
   p.dzh = b.f(rows * align_up(p.latent, 4));
@@ -367,7 +375,7 @@ __global__ void act_finalize_kernel(const float* __restrict__ mean_in, int mean_
 struct LossArgs {
   const float* mean; int mean_ld; const float* std; const float* value; const float* zp; int zld; const float* zh;
   const float* actions; const float* old_logp; const float* old_values; const float* returns; const float* adv; const int64_t* idx;
-  float* g_leg; int gleg_ld; float* g_arm; int garm_ld; float* g_vl; float* g_va; float* g_z;
+  float* g_leg; int gleg_ld; float* g_arm; int garm_ld; float* g_vl; float* g_va; int gv_ld; float* g_z;
   float* grad_std; float* losses;
   int rows, n_leg, n_act, latent;
   float clip, c_value, c_ent, c_reg, rho;
@@ -443,8 +451,12 @@ __global__ void __launch_bounds__(128) ppo_loss_kernel(const LossArgs a) {
       }
       gv[c] *= a.c_value * inv2m;
     }
-    a.g_vl[r] = gv[0];
-    a.g_va[r] = gv[1];
+    a.g_vl[(int64_t)r * a.gv_ld] = gv[0];
+    a.g_va[(int64_t)r * a.gv_ld] = gv[1];
+    // pad columns are read as (zero-weighted) operand columns by the tensor-core backward: keep them finite
+    for (int i = 2; i < a.gv_ld; ++i) a.g_vl[(int64_t)r * a.gv_ld + i] = 0.0f;
+    for (int i = a.n_leg; i < a.gleg_ld; ++i) a.g_leg[(int64_t)r * a.gleg_ld + i] = 0.0f;
+    for (int i = a.n_act - a.n_leg; i < a.garm_ld; ++i) a.g_arm[(int64_t)r * a.garm_ld + i] = 0.0f;
     // privileged-latent regulariser PPO:174-177
     float nrm = 0.0f;
     for (int i = 0; i < a.latent; ++i) {
@@ -530,6 +542,108 @@ static int head_backward(const float* P, float* grad, RowMat G_out, int n_out, i
   return DWBC_OK;
 }
 
+// ---- fused backward (TF32 path): all data-gradient GEMMs of the critic in one launch and of the actor + privileged
+// encoder in another (mlp_chain.cuh, backward ops); the per-layer pre-activation gradients they leave behind feed the
+// weight-gradient GEMMs (gemm_tc2.cuh, MN-major operands).
+struct HeadDesc { int nl; const int32_t* dims; const int64_t* ow; const int64_t* ob; float* const* acts; float* const* dz; RowMat g_out; int n_out; };
+
+// data-gradient ops of one head, last layer first; the trunk gradient accumulates in TMEM slot 1 across the two heads
+static void chain_head_bwd(ChainBuilder& b, const float* P, const HeadDesc& hd, int a_col0, int k0, int kwin, int trunk_dim, const float* trunk,
+                           bool second, float* dz_trunk) {
+  for (int l = hd.nl; l >= 0; --l) {
+    const int in = l == 0 ? trunk_dim : hd.dims[l - 1];
+    const int out = l == hd.nl ? hd.n_out : hd.dims[l];
+    const bool from_narrow = l == hd.nl;
+    if (l > 0) {
+      b.bwd(P + hd.ow[l], in, in, out, from_narrow ? k0 : 0, from_narrow ? kwin : out, ACT_ELU, hd.acts[l - 1], in, nullptr, 0,
+            from_narrow ? 2 : 0, from_narrow ? a_col0 : 0, 0, hd.dz[l - 1], in, 0, 0, 0);
+    } else {
+      b.bwd(P + hd.ow[0], in, in, out, from_narrow ? k0 : 0, from_narrow ? kwin : out, ACT_ELU, trunk, trunk_dim, nullptr, 0,
+            from_narrow ? 2 : 0, from_narrow ? a_col0 : 0, 0, second ? dz_trunk : nullptr, trunk_dim, 1, second ? 1 : 0, second ? 0 : 1);
+    }
+  }
+}
+
+static int head_wgrad(float* grad, const HeadDesc& hd, RowMat trunk, int trunk_dim, int rows, cudaStream_t st) {
+  for (int l = hd.nl; l >= 0; --l) {
+    const int in = l == 0 ? trunk_dim : hd.dims[l - 1];
+    RowMat G = l == hd.nl ? hd.g_out : rowmat(hd.dz[l], hd.dims[l]);
+    const int gout = l == hd.nl ? hd.n_out : hd.dims[l];
+    RowMat X = l == 0 ? trunk : rowmat(hd.acts[l - 1], hd.dims[l - 1]);
+    TRY(linear_bwd_weight(G, X, grad + hd.ow[l], in, grad + hd.ob[l], rows, gout, in, st));
+  }
+  return DWBC_OK;
+}
+
+static int backward_chains(const DwbcNetCfg& n, const float* P, float* grad, const DwbcStorage* s, const int64_t* idx, int rows, const Plan& p,
+                           cudaStream_t st) {
+  const int Lld = (int)align_up(p.latent, 4);
+  const int gleg_ld = (int)align_up(n.n_leg, 4), garm_ld = (int)align_up(n.n_arm, 4);
+  PackList pl{};
+  pl.out = p.wpack + (int64_t)CH_MAX_PACK * (CH_WBUF + 64);      // second half of the pack buffer (the forward images stay valid)
+  int64_t off = 0;
+  ChainBuilder C(&pl, &off, rows), A(&pl, &off, rows);
+  // ---- critic ----
+  const int cnb = n.n_critic_layers, ctd = n.critic_dims[cnb - 1];
+  HeadDesc cl{n.n_leg_layers, n.leg_dims, n.off_cleg_w, n.off_cleg_b, p.cl, p.dzc_l, rowmat(p.g_vl, 4), 1};
+  HeadDesc ca{n.n_arm_layers, n.arm_dims, n.off_carm_w, n.off_carm_b, p.ca, p.dzc_a, rowmat(p.g_va, 4), 1};
+  C.load(rowmat(p.g_vl, 4), 4, 2, 0, 8);
+  chain_head_bwd(C, P, cl, 0, 0, 8, ctd, p.cb[cnb - 1], false, nullptr);
+  chain_head_bwd(C, P, ca, 0, 1, 8, ctd, p.cb[cnb - 1], true, p.dzc_b[cnb - 1]);
+  for (int l = cnb - 1; l >= 1; --l)
+    C.bwd(P + n.off_critic_w[l], n.critic_dims[l - 1], n.critic_dims[l - 1], n.critic_dims[l], 0, n.critic_dims[l], ACT_ELU, p.cb[l - 1],
+          n.critic_dims[l - 1], nullptr, 0, 0, 0, 0, p.dzc_b[l - 1], n.critic_dims[l - 1], 0, 0, 0);
+  // ---- actor + privileged encoder ----
+  const int anb = n.n_actor_layers, atd = n.actor_dims[anb - 1];
+  HeadDesc al{n.n_leg_layers, n.leg_dims, n.off_aleg_w, n.off_aleg_b, p.al, p.dza_l, rowmat(p.g_leg, gleg_ld), n.n_leg};
+  HeadDesc aa{n.n_arm_layers, n.arm_dims, n.off_aarm_w, n.off_aarm_b, p.aa, p.dza_a, rowmat(p.g_arm, garm_ld), n.n_arm};
+  const int kw_leg = (gleg_ld + 7) & ~7, kw_arm = (garm_ld + 7) & ~7;
+  A.load(rowmat(p.g_leg, gleg_ld), gleg_ld, 2, 0, kw_leg);
+  A.load(rowmat(p.g_arm, garm_ld), garm_ld, 2, kw_leg, kw_leg + kw_arm);
+  chain_head_bwd(A, P, al, 0, 0, kw_leg, atd, p.ab[anb - 1], false, nullptr);
+  chain_head_bwd(A, P, aa, kw_leg, 0, kw_arm, atd, p.ab[anb - 1], true, p.dza_b[anb - 1]);
+  for (int l = anb - 1; l >= 1; --l)
+    A.bwd(P + n.off_actor_w[l], n.actor_dims[l - 1], n.actor_dims[l - 1], n.actor_dims[l], 0, n.actor_dims[l], ACT_ELU, p.ab[l - 1],
+          n.actor_dims[l - 1], nullptr, 0, 0, 0, 0, p.dza_b[l - 1], n.actor_dims[l - 1], 0, 0, 0);
+  const int in0 = n.num_prop + p.latent, np = n.n_priv_layers;
+  float* z = p.priv[np - 1];
+  // dL/dz = policy path through the latent columns of backbone layer 0 + privileged-latent regulariser (g_z), through the encoder's last ELU
+  A.bwd(P + n.off_actor_w[0] + n.num_prop, in0, p.latent, n.actor_dims[0], 0, n.actor_dims[0], ACT_ELU, z, Lld, p.g_z, Lld, 0, 0, 0, p.dzp[np - 1],
+        Lld, 0, 0, 0);
+  for (int l = np - 1; l >= 1; --l) {
+    const int in = n.priv_dims[l - 1], ldin = (int)align_up(in, 4);
+    A.bwd(P + n.off_priv_w[l], in, in, n.priv_dims[l], 0, n.priv_dims[l], ACT_ELU, p.priv[l - 1], ldin, nullptr, 0, 0, 0, 0, p.dzp[l - 1], ldin, 0, 0, 0);
+  }
+  if (!C.ok || !A.ok || kw_leg + kw_arm > 32) return DWBC_ERR_UNSUPPORTED;
+  TRY(launch_pack(pl, st));
+  TRY(launch_chain(C.pr, st));
+  TRY(launch_chain(A.pr, st));
+  // ---- weight gradients ----
+  RowMat obs_all = rowmat_gather(s->observations, idx, s->obs_stride);
+  TRY(head_wgrad(grad, cl, rowmat(p.cb[cnb - 1], ctd), ctd, rows, st));
+  TRY(head_wgrad(grad, ca, rowmat(p.cb[cnb - 1], ctd), ctd, rows, st));
+  for (int l = cnb - 1; l >= 0; --l) {
+    const int in = l == 0 ? n.num_prop + n.num_priv : n.critic_dims[l - 1];
+    TRY(linear_bwd_weight(rowmat(p.dzc_b[l], n.critic_dims[l]), l == 0 ? obs_all : rowmat(p.cb[l - 1], in), grad + n.off_critic_w[l], in,
+                          grad + n.off_critic_b[l], rows, n.critic_dims[l], in, st));
+  }
+  TRY(head_wgrad(grad, al, rowmat(p.ab[anb - 1], atd), atd, rows, st));
+  TRY(head_wgrad(grad, aa, rowmat(p.ab[anb - 1], atd), atd, rows, st));
+  for (int l = anb - 1; l >= 1; --l)
+    TRY(linear_bwd_weight(rowmat(p.dza_b[l], n.actor_dims[l]), rowmat(p.ab[l - 1], n.actor_dims[l - 1]), grad + n.off_actor_w[l], n.actor_dims[l - 1],
+                          grad + n.off_actor_b[l], rows, n.actor_dims[l], n.actor_dims[l - 1], st));
+  RowMat G0 = rowmat(p.dza_b[0], n.actor_dims[0]);
+  TRY(linear_bwd_weight(G0, obs_all, grad + n.off_actor_w[0], in0, grad + n.off_actor_b[0], rows, n.actor_dims[0], n.num_prop, st));
+  TRY(linear_bwd_weight(G0, rowmat(z, Lld), grad + n.off_actor_w[0] + n.num_prop, in0, nullptr, rows, n.actor_dims[0], p.latent, st));
+  for (int l = np - 1; l >= 0; --l) {
+    const int in = l == 0 ? n.num_priv : n.priv_dims[l - 1];
+    RowMat X = l == 0 ? rowmat_gather(s->observations + n.num_prop, idx, s->obs_stride) : rowmat(p.priv[l - 1], (int)align_up(in, 4));
+    TRY(linear_bwd_weight(rowmat(p.dzp[l], (int)align_up(n.priv_dims[l], 4)), X, grad + n.off_priv_w[l], in, grad + n.off_priv_b[l], rows,
+                          n.priv_dims[l], in, st));
+  }
+  return DWBC_OK;
+}
+
 }  // namespace dwbc
 
 using namespace dwbc;
@@ -608,7 +722,7 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   LossArgs a{};
   a.mean = p.mean; a.mean_ld = p.mean_ld; a.std = P + n.off_std; a.value = p.value; a.zp = z; a.zld = Lld; a.zh = p.zh;
   a.actions = s->actions; a.old_logp = s->log_prob; a.old_values = s->values; a.returns = s->returns; a.adv = s->advantages; a.idx = idx;
-  a.g_leg = p.g_leg; a.gleg_ld = gleg_ld; a.g_arm = p.g_arm; a.garm_ld = garm_ld; a.g_vl = p.g_vl; a.g_va = p.g_va; a.g_z = p.g_z;
+  a.g_leg = p.g_leg; a.gleg_ld = gleg_ld; a.g_arm = p.g_arm; a.garm_ld = garm_ld; a.g_vl = p.g_vl; a.g_va = p.g_va; a.gv_ld = 4; a.g_z = p.g_z;
   a.grad_std = grad + n.off_std; a.losses = losses_out;
   a.rows = rows; a.n_leg = n.n_leg; a.n_act = n.n_leg + n.n_arm; a.latent = p.latent;
   a.clip = hp->clip_param; a.c_value = hp->value_loss_coef; a.c_ent = hp->entropy_coef; a.c_reg = hp->priv_reg_coef; a.rho = hp->mixing_ratio;
@@ -616,13 +730,14 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   ppo_loss_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a);
   DWBC_LAUNCH_CHECK();
 
+  if (chain_usable(n, p, s->observations, s->obs_stride) && !getenv("DWBC_NO_BWD_CHAIN")) return backward_chains(n, P, grad, s, idx, rows, p, st);
   // ---- critic backward ----
   {
     const int nb = n.n_critic_layers, tdim = n.critic_dims[nb - 1];
     RowMat trunk = rowmat(p.cb[nb - 1], tdim);
-    TRY(head_backward(P, grad, rowmat(p.g_vl, 1), 1, n.n_leg_layers, n.leg_dims, n.off_cleg_w, n.off_cleg_b, p.cl, trunk, tdim, p.d2, 0, 0,
+    TRY(head_backward(P, grad, rowmat(p.g_vl, 4), 1, n.n_leg_layers, n.leg_dims, n.off_cleg_w, n.off_cleg_b, p.cl, trunk, tdim, p.d2, 0, 0,
                       p.d0, p.d1, rows, st));
-    TRY(head_backward(P, grad, rowmat(p.g_va, 1), 1, n.n_arm_layers, n.arm_dims, n.off_carm_w, n.off_carm_b, p.ca, trunk, tdim, p.d2, 1, 1,
+    TRY(head_backward(P, grad, rowmat(p.g_va, 4), 1, n.n_arm_layers, n.arm_dims, n.off_carm_w, n.off_carm_b, p.ca, trunk, tdim, p.d2, 1, 1,
                       p.d0, p.d1, rows, st));
     RowMat G = rowmat(p.d2, tdim);
     int gout = tdim;
