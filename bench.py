@@ -116,8 +116,10 @@ class Workload:
         self.host_inputs = host_inputs
         if host_inputs:
             self.host_pool = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in self.pool]
-            self.dev_in = {k: torch.empty_like(v) for k, v in self.pool[0].items()}
-            self.env.bind_sim(**self.dev_in)
+            # two device-side input sets: the copy engine fills one (copy stream) while the kernels of the previous env step read the other
+            self.dev_in = [{k: torch.empty_like(v) for k, v in self.pool[0].items()} for _ in range(2)]
+            self.copy_stream = torch.cuda.Stream(device=device)
+            self.env.bind_sim(**self.dev_in[0])
             self.host_out = torch.empty(n_envs, 3, dtype=torch.float32).pin_memory()
             self.dev_out = torch.empty(n_envs, 3, device=device)
         self.k1_events = []
@@ -131,12 +133,29 @@ class Workload:
         if obs.data_ptr() != alg.storage.obs_row(0).data_ptr():
             alg.storage.obs_row(0).copy_(obs)            # carry obs_T of the previous iteration into row 0
             obs = alg.storage.obs_row(0)
+        if self.host_inputs:
+            main = torch.cuda.current_stream()
+            copied = [torch.cuda.Event() for _ in range(T)]
+            consumed = [torch.cuda.Event() for _ in range(T)]
+
+            def h2d(t):                                   # this step's simulator state: pinned host -> device set t & 1, on the copy stream
+                with torch.cuda.stream(self.copy_stream):
+                    if t >= 2:
+                        self.copy_stream.wait_event(consumed[t - 2])      # the kernels of step t-2 have finished reading this set
+                    else:
+                        self.copy_stream.wait_stream(main)                # (first two steps: everything issued before this iteration)
+                    for k, dst in self.dev_in[t & 1].items():
+                        dst.copy_(self.host_pool[t][k], non_blocking=True)
+                    copied[t].record(self.copy_stream)
+            h2d(0)
         for t in range(T):
+            if self.host_inputs and t + 1 < T:
+                h2d(t + 1)                                # overlaps the policy inference and the post-physics kernel of step t
             actions = alg.act(obs, obs, False)
             # --- physics stand-in: Isaac Gym would simulate and refresh these tensors in place ---
             if self.host_inputs:
-                for k, dst in self.dev_in.items():
-                    dst.copy_(self.host_pool[t][k], non_blocking=True)
+                main.wait_event(copied[t])
+                env.bind_sim(**self.dev_in[t & 1])
             else:
                 env.bind_sim(**self.pool[t])
             env.set_obs_target(alg.storage.obs_row(t + 1))
@@ -150,6 +169,8 @@ class Workload:
             else:
                 env.post_physics_step()
             obs = env.obs_buf
+            if self.host_inputs:
+                consumed[t].record(main)
             alg.process_env_step(env.rew_buf, env.arm_rew_buf, env.reset_buf, env.extras)
             if self.host_inputs:                      # the step's result goes back to the host
                 self.dev_out[:, 0], self.dev_out[:, 1], self.dev_out[:, 2] = env.rew_buf, env.arm_rew_buf, env.reset_buf.float()

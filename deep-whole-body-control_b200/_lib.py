@@ -103,7 +103,7 @@ class PpoHyper(C.Structure):
 
 class Storage(C.Structure):
     _fields_ = [("observations", vp), ("obs_stride", i64), ("actions", vp), ("values", vp), ("returns", vp),
-                ("advantages", vp), ("log_prob", vp)]
+                ("advantages", vp), ("log_prob", vp), ("hist_latent", vp), ("hist_latent_ld", i64)]
 
 
 class DwbcError(RuntimeError):
@@ -123,6 +123,7 @@ _SIGS = {
     "dwbc_normalize_advantages": [vp, vp, i64, vp],
     "dwbc_policy_act": [vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp],
     "dwbc_critic_values": [vp, vp, vp, i64, vp, i32, vp, vp],
+    "dwbc_hist_latent": [vp, vp, vp, i64, vp, i64, i32, vp, vp],
     "dwbc_ppo_minibatch_grad": [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "dwbc_dagger_minibatch_grad": [vp, vp, vp, vp, i32, vp, vp, vp, vp],
     "dwbc_clip_adam_step": [vp, vp, vp, vp, i64, i64, vp, i32, vp, vp, vp],

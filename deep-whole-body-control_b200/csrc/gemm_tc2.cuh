@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const GemmArgs 
 
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
-      tc_mbar_init(&sh.full[i], T2_PROD);
+      tc_mbar_init(&sh.full[i], kMode == GEMM_BWD_WGT ? T2_PROD + T2_EPI : T2_PROD);
       // weight-gradient mode: a stage is released by the MMA commit plus, when a bias gradient is wanted, one lane of each of the 4 epilogue warps
       tc_mbar_init(&sh.empty[i], kMode == GEMM_BWD_WGT ? (g.dbias != nullptr ? 5 : 1) : T2_EPI);
     }
@@ -322,44 +322,49 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const GemmArgs 
     const int64_t k_begin = (int64_t)blockIdx.x * g.k_chunk;      // one slab per CTA (grid == items)
     const int64_t k_end = min((int64_t)g.K, k_begin + g.k_chunk);
     const int nch = (int)((k_end - k_begin + T2_WCH - 1) / T2_WCH);
-    if (warp < 4) {
-      const int ptid = tid;
+    // all eight non-MMA warps issue the operand copies (the copy issue rate of four warps was the bottleneck); the four
+    // epilogue warps additionally sum the bias gradient of the PREVIOUS chunk after issuing the current one.
+    auto fill_chunk = [&](int c, int pt) {
       const bool fastA = (vecA & 1) && (Mo & 3) == 0, fastB = (vecB & 1) && (Ni & 3) == 0;
-      for (int c = 0; c < nch; ++c) {
-        const int s = c % 3;
-        const int64_t k0 = k_begin + (int64_t)c * T2_WCH;
-        const int nk = (int)min((int64_t)T2_WCH, k_end - k0);
-        t2_pbar();
-        if (ptid < T2_WCH) { sh.rowoff[ptid] = ptid < nk ? (g.A.row(k0 + ptid) - g.A.p) : 0; sh.rowoff[64 + ptid] = ptid < nk ? (g.B.row(k0 + ptid) - g.B.p) : 0; }
-        tc_mbar_wait(&sh.empty[s], ((c / 3) & 1) ^ 1);
-        t2_pbar();
-        for (int op = 0; op < 2; ++op) {
-          float* dst = t2_smem + (2 * s + op) * TILE;
-          const float* base = op == 0 ? g.A.p : g.B.p;
-          const int64_t* ro = sh.rowoff + 64 * op;
-          const int ncol = op == 0 ? Mo : Ni;
-          if (op == 0 ? fastA : fastB) {
-            const int cpr = ncol >> 2;                          // 16-byte pieces per row
-            const uint32_t d0 = tc_smem_u32(dst);
-            const bool pow2 = (cpr & (cpr - 1)) == 0;
-            const int sh2 = 31 - __clz(cpr);
-            for (int i = ptid; i < T2_WCH * cpr; i += T2_PROD) {
-              const int k = pow2 ? (i >> sh2) : i / cpr, cc = i - k * cpr;          // row, piece
-              const float* src = k < nk ? base + ro[k] + 4 * cc : base;
-              const uint32_t off = (uint32_t)((cc >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((cc >> 1) & 3) ^ (k & 3)) << 5) + ((cc & 1) << 4));
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + off), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
-            }
-          } else {
-            for (int i = ptid; i < T2_WCH * ncol; i += T2_PROD) {
-              const int k = i / ncol, f = i - k * ncol;
-              const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
-              dst[off] = k < nk ? base[ro[k] + f] : 0.0f;
-            }
+      const int s = c % 3;
+      const int64_t k0 = k_begin + (int64_t)c * T2_WCH;
+      const int nk = (int)min((int64_t)T2_WCH, k_end - k0);
+      asm volatile("bar.sync 4, 256;" ::: "memory");      // row-offset table of the previous chunk no longer read
+      if (pt < T2_WCH) sh.rowoff[pt] = pt < nk ? (g.A.row(k0 + pt) - g.A.p) : 0;
+      else if (pt < 2 * T2_WCH) sh.rowoff[pt] = (pt - T2_WCH) < nk ? (g.B.row(k0 + pt - T2_WCH) - g.B.p) : 0;
+      tc_mbar_wait(&sh.empty[s], ((c / 3) & 1) ^ 1);
+      asm volatile("bar.sync 4, 256;" ::: "memory");
+      for (int op = 0; op < 2; ++op) {
+        float* dst = t2_smem + (2 * s + op) * TILE;
+        const float* base = op == 0 ? g.A.p : g.B.p;
+        const int64_t* ro = sh.rowoff + 64 * op;
+        const int ncol = op == 0 ? Mo : Ni;
+        if (op == 0 ? fastA : fastB) {
+          const int cpr = ncol >> 2;                          // 16-byte pieces per row
+          const uint32_t d0 = tc_smem_u32(dst);
+          const bool pow2 = (cpr & (cpr - 1)) == 0;
+          const int sh2 = 31 - __clz(cpr);
+          for (int i = pt; i < T2_WCH * cpr; i += 256) {
+            const int k = pow2 ? (i >> sh2) : i / cpr, cc = i - k * cpr;          // row, piece
+            const float* src = k < nk ? base + ro[k] + 4 * cc : base;
+            const uint32_t off = (uint32_t)((cc >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((cc >> 1) & 3) ^ (k & 3)) << 5) + ((cc & 1) << 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + off), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
+          }
+        } else {
+          for (int i = pt; i < T2_WCH * ncol; i += 256) {
+            const int k = i / ncol, f = i - k * ncol;
+            const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
+            dst[off] = k < nk ? base[ro[k] + f] : 0.0f;
           }
         }
-        // asynchronous arrival: the stage is signalled when this thread's copies have landed, the producer moves on to the next stage
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.full[s])) : "memory");
-        if (ptid == 0) T2_STAMP(1 + c);
+      }
+      // asynchronous arrival: the stage is signalled when this thread's copies have landed, the thread moves on
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.full[s])) : "memory");
+    };
+    if (warp < 4) {
+      for (int c = 0; c < nch; ++c) {
+        fill_chunk(c, tid);
+        if (tid == 0) T2_STAMP(1 + c);
       }
     } else if (warp == 4) {
       if (lane == 0) {
@@ -384,21 +389,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1) gemm_tc2_kernel(const GemmArgs 
       const int et = tid - (T2_PROD + 32);             // 0..127: output feature whose bias gradient / accumulator row this thread owns
       const int q = warp & 3;
       float bsum = 0.0f;
-      if (g.dbias != nullptr) {
-        const int fo = (et >> 5) * 128 + (et & 7);     // float offset of feature et inside row 0 of its atom (before the chunk swizzle)
-        const int c32 = (et & 31) >> 3;
-        for (int c = 0; c < nch; ++c) {
-          const int s = c % 3;
-          tc_mbar_wait(&sh.full[s], (c / 3) & 1);
-          const float* gt = t2_smem + (2 * s) * TILE;
-          if (et < Mo) {
+      const int fo = (et >> 5) * 128 + (et & 7);       // float offset of feature et inside row 0 of its atom (before the chunk swizzle)
+      const int c32 = (et & 31) >> 3;
+      auto bias_chunk = [&](int c) {
+        const int s = c % 3;
+        tc_mbar_wait(&sh.full[s], (c / 3) & 1);
+        const float* gt = t2_smem + (2 * s) * TILE;
+        if (et < Mo) {
 #pragma unroll 8
-            for (int k = 0; k < T2_WCH; ++k) bsum += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
-          }
-          __syncwarp();
-          if (lane == 0) t2_arrive(&sh.empty[s]);
+          for (int k = 0; k < T2_WCH; ++k) bsum += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
         }
+        __syncwarp();
+        if (lane == 0) t2_arrive(&sh.empty[s]);
+      };
+      for (int c = 0; c < nch; ++c) {
+        fill_chunk(c, T2_PROD + et);
+        if (g.dbias != nullptr && c > 0) bias_chunk(c - 1);
       }
+      if (g.dbias != nullptr && nch > 0) bias_chunk(nch - 1);
       if (nch > 0) {
         if (et == 0) T2_STAMP(32);
         if (g.dbias && et < Mo) atomicAdd(g.dbias + et, bsum);

@@ -373,7 +373,7 @@ __global__ void act_finalize_kernel(const float* __restrict__ mean_in, int mean_
 
 // ---- PPO loss and its derivative w.r.t. the network outputs (PPO:166-221) ----------------------
 struct LossArgs {
-  const float* mean; int mean_ld; const float* std; const float* value; const float* zp; int zld; const float* zh;
+  const float* mean; int mean_ld; const float* std; const float* value; const float* zp; int zld; const float* zh; int64_t zh_ld; int zh_by_src;
   const float* actions; const float* old_logp; const float* old_values; const float* returns; const float* adv; const int64_t* idx;
   float* g_leg; int gleg_ld; float* g_arm; int garm_ld; float* g_vl; float* g_va; int gv_ld; float* g_z;
   float* grad_std; float* losses;
@@ -459,15 +459,16 @@ __global__ void __launch_bounds__(128) ppo_loss_kernel(const LossArgs a) {
     for (int i = a.n_act - a.n_leg; i < a.garm_ld; ++i) a.g_arm[(int64_t)r * a.garm_ld + i] = 0.0f;
     // privileged-latent regulariser PPO:174-177
     float nrm = 0.0f;
+    const float* zhr = a.zh + (a.zh_by_src ? src : (int64_t)r) * a.zh_ld;     // precomputed per storage row, or per mini-batch row
     for (int i = 0; i < a.latent; ++i) {
-      const float d = a.zp[(int64_t)r * a.zld + i] - a.zh[(int64_t)r * a.zld + i];
+      const float d = a.zp[(int64_t)r * a.zld + i] - zhr[i];
       nrm += d * d;
     }
     nrm = sqrtf(nrm);
     l_reg = nrm;
     const float s = nrm > 0.0f ? a.c_reg * invm / nrm : 0.0f;
     for (int i = 0; i < a.latent; ++i)
-      a.g_z[(int64_t)r * a.zld + i] = s * (a.zp[(int64_t)r * a.zld + i] - a.zh[(int64_t)r * a.zld + i]);
+      a.g_z[(int64_t)r * a.zld + i] = s * (a.zp[(int64_t)r * a.zld + i] - zhr[i]);
   }
   // block reductions -> one atomic per CTA per quantity
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -693,6 +694,16 @@ extern "C" int dwbc_critic_values(const DwbcNetCfg* net, const float* params, co
   return critic_forward(*net, params, obs, nullptr, obs_stride, rows, p, values, (cudaStream_t)stream);
 }
 
+extern "C" int dwbc_hist_latent(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, float* out, int64_t ld_out,
+                                int32_t rows, void* workspace, dwbc_stream_t stream) {
+  TRY(check_net(net));
+  if (!params || !obs || !out || !workspace || rows <= 0) return DWBC_ERR_ARG;
+  Plan p = make_plan(*net, rows, workspace);
+  if (ld_out != align_up(p.latent, 4)) return DWBC_ERR_ARG;
+  p.zh = out;
+  return hist_forward(*net, params, obs, nullptr, obs_stride, rows, p, (cudaStream_t)stream);
+}
+
 extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* params, const DwbcStorage* s, const int64_t* idx, int32_t M,
                                        const DwbcPpoHyper* hp, float* grad, float* losses_out, void* workspace, dwbc_stream_t stream) {
   TRY(check_net(net));
@@ -710,7 +721,7 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   // forward (the reference evaluates the actor 3x and the priv encoder 3x per mini-batch,
   // PPO:166,174,230; identical values, so each is evaluated once here)
   float* z = p.priv[n.n_priv_layers - 1];
-  TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));           // PPO:175-176 (no grad)
+  if (!s->hist_latent) TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));           // PPO:175-176 (no grad)
   if (chain_usable(n, p, s->observations, s->obs_stride)) {
     TRY(forward_chains(n, P, s->observations, idx, s->obs_stride, rows, nullptr, Lld, p, p.value, true, true, true, st));
   } else {
@@ -720,7 +731,7 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   }
 
   LossArgs a{};
-  a.mean = p.mean; a.mean_ld = p.mean_ld; a.std = P + n.off_std; a.value = p.value; a.zp = z; a.zld = Lld; a.zh = p.zh;
+  a.mean = p.mean; a.mean_ld = p.mean_ld; a.std = P + n.off_std; a.value = p.value; a.zp = z; a.zld = Lld; a.zh = s->hist_latent ? s->hist_latent : p.zh; a.zh_ld = s->hist_latent ? s->hist_latent_ld : Lld; a.zh_by_src = s->hist_latent ? 1 : 0;
   a.actions = s->actions; a.old_logp = s->log_prob; a.old_values = s->values; a.returns = s->returns; a.adv = s->advantages; a.idx = idx;
   a.g_leg = p.g_leg; a.gleg_ld = gleg_ld; a.g_arm = p.g_arm; a.garm_ld = garm_ld; a.g_vl = p.g_vl; a.g_va = p.g_va; a.gv_ld = 4; a.g_z = p.g_z;
   a.grad_std = grad + n.off_std; a.losses = losses_out;

@@ -76,6 +76,7 @@ class FusedPPO:
         self.dagger_update_freq = dagger_update_freq
         self.counter = 0
         self.world_size, self.process_group = world_size, process_group
+        self._zh_all = None
         if precision not in ("fp32", "tf32"):
             raise L.DwbcError("precision must be 'fp32' (CUDA-core GEMMs, parity anchor) or 'tf32' (tcgen05 tensor cores)")
         self.precision = precision
@@ -209,6 +210,18 @@ class FusedPPO:
         ws = self._workspace(mbs)
         self._losses.zero_()
         k = 0
+        # The regulariser target z_hist (PPO:175-176) is detached, so update() never moves the history encoder (zero gradient ->
+        # zero Adam step): evaluate it once per storage row instead of once per (epoch, row).
+        total = s.num_envs * s.num_transitions_per_env
+        lld = (ac.priv_dims[-1] + 3) // 4 * 4
+        if self._zh_all is None or self._zh_all.shape[0] != total:
+            self._zh_all = torch.zeros(total, lld, device=self.device)
+        obs_flat = s.observations.view(total, -1)
+        for r0 in range(0, total, mbs):
+            nrow = min(mbs, total - r0)
+            L.check(self._lib.dwbc_hist_latent(C.addressof(ac.net_cfg), L.ptr(ac.flat), L.ptr(obs_flat[r0:]), obs_flat.stride(0),
+                                               L.ptr(self._zh_all[r0:]), lld, nrow, L.ptr(ws), L.stream_ptr()), "dwbc_hist_latent")
+        s.set_hist_latent(self._zh_all)
         for batch_idx in s.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs, indices):
             L.check(self._lib.dwbc_ppo_minibatch_grad(C.addressof(ac.net_cfg), L.ptr(ac.flat), s.c_struct_ptr(), L.ptr(batch_idx), mbs,
                                                       C.addressof(hp), L.ptr(self.grad), L.ptr(self._losses), L.ptr(ws), L.stream_ptr()),
@@ -225,6 +238,7 @@ class FusedPPO:
             k += 1
         num_updates = self.num_learning_epochs * self.num_mini_batches
         losses = (self._losses / num_updates).tolist()                                   # single sync per update
+        s.set_hist_latent(None)
         s.clear()
         value_mixing_ratio, priv_reg_coef = hp.mixing_ratio, hp.priv_reg_coef
         self.counter += 1                                                                 # PPO:259

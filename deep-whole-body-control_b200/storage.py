@@ -51,6 +51,13 @@ class FusedRolloutStorage:
         self._c.observations, self._c.obs_stride = self.observations.data_ptr(), obs_shape[0]
         self._c.actions, self._c.values, self._c.returns = self.actions.data_ptr(), self.values.data_ptr(), self.returns.data_ptr()
         self._c.advantages, self._c.log_prob = self.advantages.data_ptr(), self.actions_log_prob.data_ptr()
+        self._c.hist_latent, self._c.hist_latent_ld = None, 0
+        self._hist_latent = None
+
+    def set_hist_latent(self, z):
+        """Precomputed history latent of every storage row [T*N, ld] (or None): see DwbcStorage.hist_latent."""
+        self._hist_latent = z
+        self._c.hist_latent, self._c.hist_latent_ld = (None, 0) if z is None else (z.data_ptr(), z.stride(0))
 
     def obs_row(self, t):
         return self._obs_all[t]

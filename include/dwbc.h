@@ -261,6 +261,10 @@ int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const float* obs
 int dwbc_critic_values(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, float* values,
                        int32_t rows, void* workspace, dwbc_stream_t stream);
 
+/* history-encoder latent (AC:223-225) of obs[rows, obs_stride] -> out[rows, ld_out]; ld_out = latent rounded up to 4 */
+int dwbc_hist_latent(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, float* out,
+                     int64_t ld_out, int32_t rows, void* workspace, dwbc_stream_t stream);
+
 typedef struct DwbcPpoHyper {
   float clip_param, value_loss_coef, entropy_coef, priv_reg_coef, mixing_ratio; /* PPO:178-179, 301-302 */
   int32_t use_clipped_value_loss;
@@ -272,6 +276,10 @@ typedef struct DwbcPpoHyper {
 typedef struct DwbcStorage {
   const float* observations; int64_t obs_stride;
   const float* actions; const float* values; const float* returns; const float* advantages; const float* log_prob;
+  /* optional: history-encoder latent of EVERY storage row [T*N, hist_latent_ld], precomputed with dwbc_hist_latent.
+   * PPO.update never changes the history encoder (its output is detached, PPO:175-176, so those parameters receive no
+   * gradient), hence the regulariser target of a row is the same in all epochs.  NULL: computed per mini-batch. */
+  const float* hist_latent; int64_t hist_latent_ld;
 } DwbcStorage;
 
 /* One PPO mini-batch, forward + loss + backward (PPO:166-221,244): gathers rows idx[M] from the
