@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "mlp_chain.cuh"
+#include "wgrad_group.cuh"
 
 namespace dwbc {
 
@@ -344,8 +345,9 @@ static int forward_chains(const DwbcNetCfg& n, const float* P, const float* obs,
     if (!C.ok) return DWBC_ERR_UNSUPPORTED;
   }
   TRY(launch_pack(pl, st));
-  if (actor) TRY(launch_chain(A.pr, st));
-  if (critic) TRY(launch_chain(C.pr, st));
+  if (actor && critic) TRY(launch_chain2(&A.pr, &C.pr, st));
+  else if (actor) TRY(launch_chain(A.pr, st));
+  else if (critic) TRY(launch_chain(C.pr, st));
   return DWBC_OK;
 }
 
@@ -565,15 +567,14 @@ static void chain_head_bwd(ChainBuilder& b, const float* P, const HeadDesc& hd, 
   }
 }
 
-static int head_wgrad(float* grad, const HeadDesc& hd, RowMat trunk, int trunk_dim, int rows, cudaStream_t st) {
+static void head_wgrad(WGroupBuilder& wb, float* grad, const HeadDesc& hd, RowMat trunk, int trunk_dim) {
   for (int l = hd.nl; l >= 0; --l) {
     const int in = l == 0 ? trunk_dim : hd.dims[l - 1];
     RowMat G = l == hd.nl ? hd.g_out : rowmat(hd.dz[l], hd.dims[l]);
     const int gout = l == hd.nl ? hd.n_out : hd.dims[l];
     RowMat X = l == 0 ? trunk : rowmat(hd.acts[l - 1], hd.dims[l - 1]);
-    TRY(linear_bwd_weight(G, X, grad + hd.ow[l], in, grad + hd.ob[l], rows, gout, in, st));
+    wb.add(G, X, grad + hd.ow[l], in, grad + hd.ob[l], gout, in);
   }
-  return DWBC_OK;
 }
 
 static int backward_chains(const DwbcNetCfg& n, const float* P, float* grad, const DwbcStorage* s, const int64_t* idx, int rows, const Plan& p,
@@ -617,31 +618,32 @@ static int backward_chains(const DwbcNetCfg& n, const float* P, float* grad, con
   }
   if (!C.ok || !A.ok || kw_leg + kw_arm > 32) return DWBC_ERR_UNSUPPORTED;
   TRY(launch_pack(pl, st));
-  TRY(launch_chain(C.pr, st));
-  TRY(launch_chain(A.pr, st));
-  // ---- weight gradients ----
+  TRY(launch_chain2(&A.pr, &C.pr, st));
+  // ---- weight gradients: every layer of both networks in one persistent launch (wgrad_group.cuh) ----
   RowMat obs_all = rowmat_gather(s->observations, idx, s->obs_stride);
-  TRY(head_wgrad(grad, cl, rowmat(p.cb[cnb - 1], ctd), ctd, rows, st));
-  TRY(head_wgrad(grad, ca, rowmat(p.cb[cnb - 1], ctd), ctd, rows, st));
+  WGroupBuilder wb;
+  head_wgrad(wb, grad, cl, rowmat(p.cb[cnb - 1], ctd), ctd);
+  head_wgrad(wb, grad, ca, rowmat(p.cb[cnb - 1], ctd), ctd);
   for (int l = cnb - 1; l >= 0; --l) {
     const int in = l == 0 ? n.num_prop + n.num_priv : n.critic_dims[l - 1];
-    TRY(linear_bwd_weight(rowmat(p.dzc_b[l], n.critic_dims[l]), l == 0 ? obs_all : rowmat(p.cb[l - 1], in), grad + n.off_critic_w[l], in,
-                          grad + n.off_critic_b[l], rows, n.critic_dims[l], in, st));
+    wb.add(rowmat(p.dzc_b[l], n.critic_dims[l]), l == 0 ? obs_all : rowmat(p.cb[l - 1], in), grad + n.off_critic_w[l], in, grad + n.off_critic_b[l],
+           n.critic_dims[l], in);
   }
-  TRY(head_wgrad(grad, al, rowmat(p.ab[anb - 1], atd), atd, rows, st));
-  TRY(head_wgrad(grad, aa, rowmat(p.ab[anb - 1], atd), atd, rows, st));
+  head_wgrad(wb, grad, al, rowmat(p.ab[anb - 1], atd), atd);
+  head_wgrad(wb, grad, aa, rowmat(p.ab[anb - 1], atd), atd);
   for (int l = anb - 1; l >= 1; --l)
-    TRY(linear_bwd_weight(rowmat(p.dza_b[l], n.actor_dims[l]), rowmat(p.ab[l - 1], n.actor_dims[l - 1]), grad + n.off_actor_w[l], n.actor_dims[l - 1],
-                          grad + n.off_actor_b[l], rows, n.actor_dims[l], n.actor_dims[l - 1], st));
+    wb.add(rowmat(p.dza_b[l], n.actor_dims[l]), rowmat(p.ab[l - 1], n.actor_dims[l - 1]), grad + n.off_actor_w[l], n.actor_dims[l - 1],
+           grad + n.off_actor_b[l], n.actor_dims[l], n.actor_dims[l - 1]);
   RowMat G0 = rowmat(p.dza_b[0], n.actor_dims[0]);
-  TRY(linear_bwd_weight(G0, obs_all, grad + n.off_actor_w[0], in0, grad + n.off_actor_b[0], rows, n.actor_dims[0], n.num_prop, st));
-  TRY(linear_bwd_weight(G0, rowmat(z, Lld), grad + n.off_actor_w[0] + n.num_prop, in0, nullptr, rows, n.actor_dims[0], p.latent, st));
+  wb.add(G0, obs_all, grad + n.off_actor_w[0], in0, grad + n.off_actor_b[0], n.actor_dims[0], n.num_prop);
+  wb.add(G0, rowmat(z, Lld), grad + n.off_actor_w[0] + n.num_prop, in0, nullptr, n.actor_dims[0], p.latent);
   for (int l = np - 1; l >= 0; --l) {
     const int in = l == 0 ? n.num_priv : n.priv_dims[l - 1];
     RowMat X = l == 0 ? rowmat_gather(s->observations + n.num_prop, idx, s->obs_stride) : rowmat(p.priv[l - 1], (int)align_up(in, 4));
-    TRY(linear_bwd_weight(rowmat(p.dzp[l], (int)align_up(n.priv_dims[l], 4)), X, grad + n.off_priv_w[l], in, grad + n.off_priv_b[l], rows,
-                          n.priv_dims[l], in, st));
+    wb.add(rowmat(p.dzp[l], (int)align_up(n.priv_dims[l], 4)), X, grad + n.off_priv_w[l], in, grad + n.off_priv_b[l], n.priv_dims[l], in);
   }
+  if (!wb.ok) return DWBC_ERR_UNSUPPORTED;
+  TRY(launch_wgrad_group(wb.g, rows, st));
   return DWBC_OK;
 }
 

@@ -58,6 +58,11 @@ struct ChainProg {
 };
 
 // transpose = 0: image(n, k) = w[n*ldw + (k - k0)];  transpose = 1: image(n, k) = w[(k - k0)*ldw + n];  zero outside 0 <= k - k0 < K, n < N
+// up to two independent programs over the same rows (actor and critic) share one launch: work items (tile, program) are
+// dealt round-robin to the persistent CTAs, which evens out the load (320 tiles x {9, 7} ops over 148 CTAs) and lets the two
+// networks of the rollout's act() run side by side
+struct ChainProg2 { int nprog; ChainProg p[2]; };
+
 struct PackItem { const float* w; int64_t ldw; const float* bias; int N, K, npad, kpad; int64_t dst; int transpose, k0; };
 struct PackList { int n; float* out; PackItem it[CH_MAX_PACK]; };
 
@@ -107,7 +112,7 @@ __device__ __forceinline__ void ch_bias_act(float* v, const float* bias, int nva
   }
 }
 
-__global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_constant__ ChainProg pr, const int tiles) {
+__global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_constant__ ChainProg2 pp, const int tiles) {
   extern __shared__ __align__(1024) float ch_smem[];
   __shared__ ChShared sh;
   float* buf[3] = {ch_smem, ch_smem + CH_TILE, ch_smem + 2 * CH_TILE + CH_WBUF};
@@ -128,24 +133,28 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
   if (tid == 0) T2_STAMP(62);
-  const int my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int nops = pr.n_ops;
+  const int items = tiles * pp.nprog;                 // item it = (tile it / nprog, program it % nprog)
+  const int my_tiles = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nprog = pp.nprog;
 
   if (warp == 4) {
     // ===================== weight copies + MMA issue (one thread) =====================
     if (lane == 0 && my_tiles > 0) {
       // weights of op (global index n) -> wbuf, its bias -> bias slot n & 1: the epilogue of op n still reads its bias while
       // the weights of op n+1 stream in
-      auto fetch_w = [&](int i, uint32_t nn) {
-        const uint32_t wbytes = (uint32_t)(pr.op[i].npad * pr.op[i].kpad) * 4u, bbytes = (uint32_t)pr.op[i].npad * 4u;
+      auto fetch_w = [&](const ChainOp& w, uint32_t nn) {
+        const uint32_t wbytes = (uint32_t)(w.npad * w.kpad) * 4u, bbytes = (uint32_t)w.npad * 4u;
         ch_expect_tx(&sh.w_full, wbytes + bbytes);
-        ch_bulk_g2s(wbuf, pr.op[i].wp, wbytes, &sh.w_full);
-        ch_bulk_g2s(wbuf + CH_TILE + (nn & 1) * 128, pr.op[i].wp + pr.op[i].npad * pr.op[i].kpad, bbytes, &sh.w_full);
+        ch_bulk_g2s(wbuf, w.wp, wbytes, &sh.w_full);
+        ch_bulk_g2s(wbuf + CH_TILE + (nn & 1) * 128, w.wp + w.npad * w.kpad, bbytes, &sh.w_full);
       };
-      fetch_w(0, 0);
+      fetch_w(pp.p[blockIdx.x % nprog].op[0], 0);
       uint32_t n = 0;
       const uint32_t b0 = tc_smem_u32(wbuf);
       for (int j = 0; j < my_tiles; ++j) {
+        const int it = blockIdx.x + j * gridDim.x;
+        const ChainProg& pr = pp.p[it % nprog];
+        const int nops = pr.n_ops;
         for (int i = 0; i < nops; ++i, ++n) {
           const ChainOp& o = pr.op[i];
           tc_mbar_wait(&sh.w_full, n & 1);
@@ -166,8 +175,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
           tc_commit(&sh.mma_done);
           tc_mbar_wait(&sh.mma_done, n & 1);                    // weights consumed: the buffer may be refilled while the epilogue runs
           if (n < 10) T2_STAMP(6 * n + 2);
-          if (i + 1 < nops) fetch_w(i + 1, n + 1);
-          else if (j + 1 < my_tiles) fetch_w(0, n + 1);
+          if (i + 1 < nops) fetch_w(pr.op[i + 1], n + 1);
+          else if (j + 1 < my_tiles) fetch_w(pp.p[(it + gridDim.x) % nprog].op[0], n + 1);
         }
       }
     }
@@ -182,7 +191,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
     const int r = q * 32 + lane;            // tile row of this thread
     uint32_t n = 0, nx = 0;
     for (int j = 0; j < my_tiles; ++j) {
-      const int64_t m0 = (int64_t)(blockIdx.x + j * gridDim.x) * TC_M;
+      const int it = blockIdx.x + j * gridDim.x;
+      const ChainProg& pr = pp.p[it % nprog];
+      const int nops = pr.n_ops;
+      const int64_t m0 = (int64_t)(it / nprog) * TC_M;
       const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
       if (h == 1) {
         t2_pbar();                                             // row-offset table of the previous tile no longer read
@@ -346,26 +358,35 @@ inline int launch_pack(const PackList& pl, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
 
-inline int launch_chain(const ChainProg& pr, cudaStream_t st) {
-  if (pr.M <= 0 || pr.n_ops <= 0 || pr.n_ops > CH_MAX_OPS || pr.n_loads < 0 || pr.n_loads > CH_MAX_LOADS) return DWBC_ERR_ARG;
+inline int launch_chain2(const ChainProg* a, const ChainProg* b, cudaStream_t st) {
+  ChainProg2 pp{};
+  pp.nprog = b ? 2 : 1;
+  pp.p[0] = *a;
+  if (b) pp.p[1] = *b;
+  for (int k = 0; k < pp.nprog; ++k) {
+    const ChainProg& pr = pp.p[k];
+    if (pr.M <= 0 || pr.M != pp.p[0].M || pr.n_ops <= 0 || pr.n_ops > CH_MAX_OPS || pr.n_loads < 0 || pr.n_loads > CH_MAX_LOADS) return DWBC_ERR_ARG;
+  }
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int tiles = (pr.M + TC_M - 1) / TC_M;
-  const int grid = tiles < sms ? tiles : sms;
+  const int tiles = (pp.p[0].M + TC_M - 1) / TC_M;
+  const int items = tiles * pp.nprog;
+  const int grid = items < sms ? items : sms;
   const size_t smem = (size_t)CH_SMEM_FLOATS * sizeof(float);
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DWBC_ERR_LAUNCH;
     attr = true;
   }
-  chain_fwd_kernel<<<grid, T2_THREADS, smem, st>>>(pr, tiles);
+  chain_fwd_kernel<<<grid, T2_THREADS, smem, st>>>(pp, tiles);
   ++dwbc_launch_counter;
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
+inline int launch_chain(const ChainProg& pr, cudaStream_t st) { return launch_chain2(&pr, nullptr, st); }
 
 // Small builder: keeps the pack list and the program in step.
 struct ChainBuilder {

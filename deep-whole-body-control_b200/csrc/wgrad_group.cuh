@@ -1,0 +1,218 @@
+// All weight-gradient GEMMs of one PPO mini-batch in ONE persistent launch (tcgen05, TF32, MN-major operands).
+//
+//   dW_l[out x in] += dZ_l^T X_l ,  db_l[out] += colsum(dZ_l)        for every layer l, reduction over the mini-batch rows
+//
+// Layer by layer (gemm_tc2_kernel<GEMM_BWD_WGT>) each GEMM is a 128-CTA launch of ~20 us, a third of which is the split-K
+// epilogue, plus launch gaps and tails.  Here a work item is (layer, slab of `slab` rows); the items are dealt round-robin to
+// one persistent CTA per SM, so the epilogue is amortised over 4x longer slabs and there are no gaps.
+// Operand tiles, the SWIZZLE_128B_BASE32B MN-major layout, the 8-warp cp.async fill with asynchronous barrier arrival, the
+// bias-gradient column sums and the staged vector-reduction epilogue are those of gemm_tc2.cuh (weight-gradient branch).
+#pragma once
+#include "gemm_tc2.cuh"
+
+namespace dwbc {
+
+constexpr int WG_MAX = 20;
+struct WGItem {
+  RowMat G, X;          // dZ [rows x Mo], X [rows x Ni]
+  float* dW; int64_t lddw;
+  float* db;            // nullable
+  int Mo, Ni;
+  int fastG, fastX;     // 16-byte aligned rows and width % 4 == 0: cp.async path
+};
+struct WGroup { int n, rows, slab, nslab; WGItem it[WG_MAX]; };
+
+__global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid_constant__ WGroup grp) {
+  extern __shared__ __align__(1024) float wg_smem[];
+  __shared__ T2Shared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int TILE = T2_WCH * 128;                // floats per operand tile: 64 rows x 128 features
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) {
+      tc_mbar_init(&sh.full[i], T2_PROD + T2_EPI);
+      tc_mbar_init(&sh.empty[i], 5);                // MMA commit + one lane of each of the 4 epilogue warps (bias-gradient reads)
+    }
+    tc_mbar_init(&sh.tfull[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tc_tmem_alloc(&sh.tmem_base, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+  const int items = grp.n * grp.nslab;
+  const int my_items = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  // chunk `cc` is the CTA-wide running chunk counter (stage cc % 3, use cc / 3): identical in every thread
+  auto fill_chunk = [&](const WGItem& g, int64_t k0, int nk, uint32_t cc, int pt) {
+    const int s = cc % 3;
+    asm volatile("bar.sync 4, 256;" ::: "memory");      // row-offset table of the previous chunk no longer read (and, at an item
+                                                        // boundary, the epilogue has released the stages it used as staging)
+    if (pt < T2_WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
+    else if (pt < 2 * T2_WCH) sh.rowoff[pt] = (pt - T2_WCH) < nk ? (g.X.row(k0 + pt - T2_WCH) - g.X.p) : 0;
+    tc_mbar_wait(&sh.empty[s], ((cc / 3) & 1) ^ 1);
+    asm volatile("bar.sync 4, 256;" ::: "memory");
+    for (int op = 0; op < 2; ++op) {
+      float* dst = wg_smem + (2 * s + op) * TILE;
+      const float* base = op == 0 ? g.G.p : g.X.p;
+      const int64_t* ro = sh.rowoff + 64 * op;
+      const int ncol = op == 0 ? g.Mo : g.Ni;
+      if (op == 0 ? g.fastG : g.fastX) {
+        const int cpr = ncol >> 2;                          // 16-byte pieces per row
+        const uint32_t d0 = tc_smem_u32(dst);
+        const bool pow2 = (cpr & (cpr - 1)) == 0;
+        const int sh2 = 31 - __clz(cpr);
+        for (int i = pt; i < T2_WCH * cpr; i += 256) {
+          const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;          // row, piece
+          const float* src = k < nk ? base + ro[k] + 4 * c4 : base;
+          const uint32_t off = (uint32_t)((c4 >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((c4 >> 1) & 3) ^ (k & 3)) << 5) + ((c4 & 1) << 4));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + off), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
+        }
+      } else {
+        for (int i = pt; i < T2_WCH * ncol; i += 256) {
+          const int k = i / ncol, f = i - k * ncol;
+          const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
+          dst[off] = k < nk ? base[ro[k] + f] : 0.0f;
+        }
+      }
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.full[s])) : "memory");
+  };
+
+  uint32_t cc = 0;                                     // running chunk counter
+  for (int j = 0; j < my_items; ++j) {
+    const int w = blockIdx.x + j * gridDim.x;
+    const WGItem& g = grp.it[w % grp.n];
+    const int64_t k_begin = (int64_t)(w / grp.n) * grp.slab;
+    const int64_t k_end = min((int64_t)grp.rows, k_begin + grp.slab);
+    const int nch = (int)((k_end - k_begin + T2_WCH - 1) / T2_WCH);
+    const int Mo = g.Mo, Ni = g.Ni, nipad = (Ni + 15) & ~15;
+    if (warp < 4) {
+      for (int c = 0; c < nch; ++c) {
+        const int64_t k0 = k_begin + (int64_t)c * T2_WCH;
+        fill_chunk(g, k0, (int)min((int64_t)T2_WCH, k_end - k0), cc + c, tid);
+      }
+    } else if (warp == 4) {
+      if (lane == 0) {
+        const uint32_t idesc = tc_idesc(nipad, true, true);
+        for (int c = 0; c < nch; ++c) {
+          const uint32_t u = cc + c;
+          const int s = u % 3;
+          tc_mbar_wait(&sh.full[s], (u / 3) & 1);
+          tc_fence_async_smem();          // generic-proxy writes of the producers (made visible by the barrier) -> async proxy reads of the MMA
+          tc_fence_after();
+          const uint32_t a0 = tc_smem_u32(wg_smem + (2 * s) * TILE), b0 = a0 + TILE * 4;
+          for (int kk = 0; kk < T2_WCH; kk += 8) {
+            const uint64_t ad = tc_desc(a0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
+            const uint64_t bd = tc_desc(b0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
+            tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(&sh.empty[s]);
+        }
+        tc_commit(&sh.tfull[0]);
+      }
+    } else {
+      const int et = tid - (T2_PROD + 32);             // 0..127: output feature whose bias gradient / accumulator row this thread owns
+      const int q = warp & 3;
+      float bsum = 0.0f;
+      const int fo = (et >> 5) * 128 + (et & 7);       // float offset of feature et inside row 0 of its atom (before the chunk swizzle)
+      const int c32 = (et & 31) >> 3;
+      auto bias_chunk = [&](uint32_t u) {
+        const int s = u % 3;
+        tc_mbar_wait(&sh.full[s], (u / 3) & 1);
+        const float* gt = wg_smem + (2 * s) * TILE;
+        if (g.db != nullptr && et < Mo) {
+#pragma unroll 8
+          for (int k = 0; k < T2_WCH; ++k) bsum += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
+        }
+        __syncwarp();
+        if (lane == 0) t2_arrive(&sh.empty[s]);
+      };
+      for (int c = 0; c < nch; ++c) {
+        const int64_t k0 = k_begin + (int64_t)c * T2_WCH;
+        fill_chunk(g, k0, (int)min((int64_t)T2_WCH, k_end - k0), cc + c, T2_PROD + et);
+        if (c > 0) bias_chunk(cc + c - 1);
+      }
+      if (nch > 0) {
+        bias_chunk(cc + nch - 1);
+        if (g.db && et < Mo) atomicAdd(g.db + et, bsum);
+        const int o = q * 32 + lane;
+        tc_mbar_wait(&sh.tfull[0], j & 1);
+        tc_fence_after();
+        t2_ebar();                                      // every epilogue warp is done reading G tiles (bias gradient) before the stages are reused
+        // all MMAs of this item have completed and the producers wait at the next item's first bar.sync: the operand stages
+        // become the staging tile [128][132]; the split-K partial goes out as row-contiguous vector reductions
+        float* stg = wg_smem;
+        for (int c0 = 0; c0 < nipad; c0 += 32) {
+          float v[32];
+          tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(stg + (size_t)o * T2_LDS + c0 + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+        tc_fence_before();
+        __syncwarp();                                   // warp q wrote rows q*32 .. q*32+31 and reduces exactly those rows
+        const bool v4 = (g.lddw & 3) == 0 && (Ni & 3) == 0 && (reinterpret_cast<uintptr_t>(g.dW) & 15) == 0;
+        for (int r = q * 32; r < min(q * 32 + 32, Mo); ++r) {
+          float* crow = g.dW + (int64_t)r * g.lddw;
+          if (v4) {
+            if (4 * lane < Ni) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)r * T2_LDS + 4 * lane);
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * lane), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+            }
+          } else {
+            for (int n = lane; n < Ni; n += 32) atomicAdd(crow + n, stg[(size_t)r * T2_LDS + n]);
+          }
+        }
+      }
+    }
+    cc += nch;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc_tmem_dealloc(tmem, 128);
+}
+
+struct WGroupBuilder {
+  WGroup g{};
+  bool ok = true;
+  void add(RowMat G, RowMat X, float* dW, int64_t lddw, float* db, int Mo, int Ni) {
+    if (g.n >= WG_MAX || Mo > 128 || Ni > 128 || Mo <= 0 || Ni <= 0) { ok = false; return; }
+    WGItem& it = g.it[g.n++];
+    it.G = G; it.X = X; it.dW = dW; it.lddw = lddw; it.db = db; it.Mo = Mo; it.Ni = Ni;
+    it.fastG = rowmat_vec_ok(G) && (Mo & 3) == 0;
+    it.fastX = rowmat_vec_ok(X) && (Ni & 3) == 0;
+  }
+};
+
+inline int launch_wgrad_group(WGroup& g, int rows, cudaStream_t st) {
+  if (g.n <= 0 || rows <= 0) return DWBC_ERR_ARG;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  g.rows = rows;
+  // slab length: ~4 work items per CTA, at least 4 chunks so that the epilogue stays amortised
+  int64_t total_items = (int64_t)4 * sms;
+  int64_t nslab = (total_items + g.n - 1) / g.n;
+  int64_t slab = (rows + nslab - 1) / nslab;
+  slab = (slab + T2_WCH - 1) / T2_WCH * T2_WCH;
+  if (slab < 4 * T2_WCH) slab = 4 * T2_WCH;
+  g.slab = (int)slab;
+  g.nslab = (int)((rows + slab - 1) / slab);
+  const int items = g.n * g.nslab;
+  const int grid = items < sms ? items : sms;
+  const size_t smem = (size_t)(6 * T2_WCH * 128) * sizeof(float);       // 3 stages x {G tile, X tile} = 192 KB (>= the 66 KB staging tile)
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DWBC_ERR_LAUNCH;
+    attr = true;
+  }
+  wgrad_group_kernel<<<grid, T2_THREADS, smem, st>>>(g);
+  ++dwbc_launch_counter;
+  return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
+}
+
+}  // namespace dwbc

@@ -133,6 +133,8 @@ class FusedPPO:
         self._set_precision()
         n = obs.shape[0]
         if eps is None:
+            if self._eps is None or self._eps.shape[0] != n:
+                self._eps = torch.empty(n, ac.num_leg_actions + ac.num_arm_actions, device=self.device)
             eps = self._eps.normal_(generator=self.generator)
         if s is not None and s.step < s.num_transitions_per_env and n == s.num_envs:
             t = s.step
