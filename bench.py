@@ -287,6 +287,9 @@ def run_ours(args):
                          "us_per_launch": k1_ms * 1e3, "algorithmic_bytes_per_launch": w.N * K1_BYTES_PER_ENV,
                          "timing": "CUDA events around 40 back-to-back launches queued behind a spin kernel (includes the 1-launch stats memset); "
                                    "events around single launches inside the rollout read %.1f us because the host submits slower than the kernel runs" % (k1_ms_inline * 1e3)},
+            # second half of BASELINE's metric: the ActorCritic GEMMs of update() against the tensor-core roof.  Algorithmic work =
+            # 518 808 MAC per mini-batch row (forward 195 736 incl. the history encoder, backward 323 072), 20 mini-batches.
+            "roofline_mlp": mlp_roofline(float(upd), w.N * w.T // 4, pk, args.precision),
             "clocks": clocks,
         }
         torch.cuda.synchronize()
@@ -295,6 +298,18 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def mlp_roofline(update_ms, mb_rows, pk, precision):
+    flop = 2.0 * 518808 * mb_rows * 20
+    achieved = flop / (update_ms * 1e-3) / 1e12
+    bf16 = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1426.0))      # a kernel timed inside a long step: sustained figure
+    peak = bf16 / 2 if precision == "tf32" else 72.0      # TF32 dense = half the measured bf16 rate; fp32 CUDA cores: 148 SMs x 128 FMA x 1.9 GHz
+    return {"kernels": "chain_fwd_kernel (fused forward / backward layer chains) + wgrad_group_kernel" if precision == "tf32" else "gemm_simt_kernel",
+            "bound": "tensor" if precision == "tf32" else "fp32 pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "algorithmic_gflop_per_update": flop / 1e9, "update_ms": update_ms,
+            "note": "whole update(): loss, Adam, packing and every activation store / reload included; the chains are bounded by activation traffic "
+                    "(~1.6 GB per mini-batch through L2/HBM), not by the tensor pipe"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -384,8 +399,9 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
-                    help="ActorCritic GEMM path: fp32 CUDA cores (reference precision, default) or TF32 tcgen05 tensor cores")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="ActorCritic GEMM path: TF32 tcgen05 tensor cores with fp32 accumulation (default; what north_star asks for and what the "
+                         "reference's pinned torch 1.10 does on Ampere+ GPUs, allow_tf32=True) or exact fp32 CUDA cores (parity anchor)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -28,6 +28,8 @@ constexpr int CH_TILE = 128 * 128;                 // floats per operand tile
 constexpr int CH_WBUF = 128 * 128 + 2 * 128;       // packed weight image + two bias slots (op parity)
 constexpr int CH_NARROW = 128 * 32;                // narrow input tile (buffer 2): [128 rows x 32 k], 8 pieces per row group (SBO 1024 B)
 constexpr int CH_SMEM_FLOATS = 2 * CH_TILE + CH_WBUF + CH_NARROW;
+constexpr int CH_GROUPS = 4;                       // epilogue warp groups (4 warps each, one per TMEM lane quarter)
+constexpr int CH_THREADS = 32 * (5 + 4 * (CH_GROUPS - 1));   // warps 0-3 (loads + epilogue group 1), 4 (MMA), 5-8 (group 0), 9.. (groups 2, 3)
 
 struct ChainLoad {
   RowMat src;        // rows of the source (already offset to the first column)
@@ -112,7 +114,7 @@ __device__ __forceinline__ void ch_bias_act(float* v, const float* bias, int nva
   }
 }
 
-__global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_constant__ ChainProg2 pp, const int tiles) {
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(const __grid_constant__ ChainProg2 pp, const int tiles) {
   extern __shared__ __align__(1024) float ch_smem[];
   __shared__ ChShared sh;
   float* buf[3] = {ch_smem, ch_smem + CH_TILE, ch_smem + 2 * CH_TILE + CH_WBUF};
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
     tc_mbar_init(&sh.w_full, 1);
     tc_mbar_init(&sh.ld_full, T2_PROD);
     tc_mbar_init(&sh.mma_done, 1);
-    tc_mbar_init(&sh.epi_done, T2_PROD + T2_EPI);
+    tc_mbar_init(&sh.epi_done, 128 * CH_GROUPS);
     tc_mbar_init(&sh.tile_done, T2_EPI);
     tc_mbar_init(&sh.x_full, T2_PROD);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,10 +184,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
     }
   } else {
     // ===================== LOADS (warps 0-3) + EPILOGUE (warps 0-3 and 5-8) =====================
-    // Two warps share each TMEM lane quarter (warp % 4) and split an op's 32-column chunks: group 0 (warps 5-8) takes the
-    // even chunks, group 1 (warps 0-3, idle between two tile loads otherwise) the odd ones.  A warp copies to global memory
+    // CH_GROUPS warps share each TMEM lane quarter (warp % 4) and split an op's 32-column chunks round-robin: group 0 = warps 5-8,
+    // group 1 = warps 0-3 (idle between two tile loads otherwise), groups 2, 3 = warps 9-12, 13-16.  A warp copies to global memory
     // exactly the chunks it wrote itself (128 contiguous bytes per row), so no cross-warp synchronisation is needed.
-    const int h = warp < 4 ? 1 : 0;
+    const int h = warp < 4 ? 1 : (warp < 9 ? 0 : 2 + ((warp - 9) >> 2));   // epilogue group: takes the 32-column chunks ci with ci % CH_GROUPS == h
     const int ptid = tid;                   // producer thread index (group 1 only)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;            // tile row of this thread
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
         const bool direct = o.y != nullptr && o.out_buf < 0;
         float* yrow = o.y ? o.y + (m0 + r) * o.ldy : nullptr;
         const bool yal = (o.ldy & 3) == 0 && (o.N & 3) == 0 && (reinterpret_cast<uintptr_t>(o.y) & 15) == 0;
-        for (int c0 = 32 * h; c0 < o.npad; c0 += 64) {
+        for (int c0 = 32 * h; c0 < o.npad; c0 += 32 * CH_GROUPS) {
           float v[32];
           tc_ld32(tmem + o.tslot * 128 + ((uint32_t)(q * 32) << 16) + c0, v);
           if (o.mode == 0) {
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) chain_fwd_kernel(const __grid_c
           __syncwarp();
           const int r8 = lane & 7, pp = lane >> 3;
           const float* t0 = buf[o.out_buf];
-          for (int c0 = 32 * h; c0 < o.N; c0 += 64) {
+          for (int c0 = 32 * h; c0 < o.N; c0 += 32 * CH_GROUPS) {
             if (yal) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -382,7 +384,7 @@ inline int launch_chain2(const ChainProg* a, const ChainProg* b, cudaStream_t st
     if (cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DWBC_ERR_LAUNCH;
     attr = true;
   }
-  chain_fwd_kernel<<<grid, T2_THREADS, smem, st>>>(pp, tiles);
+  chain_fwd_kernel<<<grid, CH_THREADS, smem, st>>>(pp, tiles);
   ++dwbc_launch_counter;
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
