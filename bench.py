@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)
 
     def finish(self):
         self._halt.set()
@@ -356,8 +356,8 @@ def pick_threads(n_envs=256):
     return best, cores
 
 
-def cpu_baseline(args, n_envs=256):
-    cores, host_cores = pick_threads(n_envs)
+def cpu_baseline(args, n_envs=2048):
+    cores, host_cores = pick_threads(256)
     it = make_oracle_iteration(n_envs, T_STEPS)
     it.run()
     t0 = time.perf_counter()
@@ -396,7 +396,7 @@ def run_reference(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
