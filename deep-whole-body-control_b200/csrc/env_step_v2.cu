@@ -371,7 +371,65 @@ env_step_v2_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant
   cbar();
   V2_TICK(2);
 
-  // ---- 6. scalar pass: thread per env (warp 0) ---------------------------------------------------
+  // ---- assembly of one env's observation columns (WG:966-1001, Appendix B): warp per env, lane per column.
+  // part 0 = columns that depend only on the simulator state (joint positions / velocities, last action, foot contacts,
+  // privileged mass / friction / motor strength): assembled by warps 1..6 WHILE warp 0 runs the scalar pass;
+  // part 1 = columns produced by the scalar / fix-up passes (roll-pitch, angular velocity, commands, goal, root velocity).
+  auto assemble = [&](const int e, const int part) {
+    const float* dof = sm + Ly::o_dof + e * 2 * ND;
+    const float* gs = sm + Ly::o_gs + e * DWBC_GS;
+    float* ds = sm + Ly::o_ds + e * DWBC_DS;
+    float* prop = sm + Ly::o_prop + e * P;
+    float* priv = sm + Ly::o_priv + e * NPRIV;
+    bool bad = false;
+    if (part == 0) {
+      if (lane < ND) {            // dof position / velocity columns, last_dof_vel
+        const int d = ig2r_s[lane];
+        float pos = dof[2 * d];
+        if (d == cfg.waist_dof) pos = wrap_pi(pos);
+        const float v0 = (pos - defpos_s[d]) * cfg.obs_scale_dof_pos, v1 = dof[2 * d + 1] * cfg.obs_scale_dof_vel;
+        prop[5 + lane] = v0;
+        prop[5 + ND + lane] = v1;
+        bad = !(fabsf(v0) <= c) || !(fabsf(v1) <= c);
+        ds[DWBC_DS_LAST_DOF_VEL + lane] = dof[2 * lane + 1];
+      }
+      if (lane < NA) {            // last applied action column, last_actions, motor strength
+        const float v = sm[Ly::o_ah + e * AH * NA + (AH - 1) * NA + ig2r_s[lane]];
+        prop[5 + 2 * ND + lane] = v;
+        bad = bad || !(fabsf(v) <= c);
+        ds[DWBC_DS_LAST_ACTIONS + lane] = sm[Ly::o_act + e * NA + lane];
+        priv[6 + lane] = sm[Ly::o_motor + e * NA + lane] - 1.0f;
+      }
+    }
+    {
+      constexpr int o = 5 + 2 * ND + NA;
+      float v = 0.0f;
+      int col = -1;
+      if (part == 0) {
+        if (lane < 4) {           // foot contacts (WG:1090-1098)
+          const float* f = sm + Ly::o_fs + e * 24 + 6 * (lane == 0 ? cfg.feet_perm[0] : (lane == 1 ? cfg.feet_perm[1] : (lane == 2 ? cfg.feet_perm[2] : cfg.feet_perm[3])));
+          float nrm = nsqrt(((((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) + f[3] * f[3]) + f[4] * f[4]) + f[5] * f[5]);
+          v = nrm > 1.5f ? 1.0f : 0.0f; col = o + lane;
+        } else if (lane >= 18 && lane < 23) priv[lane - 18] = sm[Ly::o_mass + e * 5 + lane - 18];
+        else if (lane == 23) priv[5] = sm[Ly::o_fric + e];
+      } else {
+        if (lane >= 4 && lane < 6) { v = sm[Ly::o_rp + 4 * e + lane - 4]; col = lane - 4; }
+        else if (lane >= 6 && lane < 9) { v = ds[DWBC_DS_BASE_ANG_VEL + lane - 6] * cfg.obs_scale_ang_vel; col = 2 + lane - 6; }
+        else if (lane >= 9 && lane < 11) { v = gs[lane - 9] * cfg.obs_scale_lin_vel; col = o + 4 + lane - 9; }
+        else if (lane == 11) { v = gs[2] * cfg.obs_scale_ang_vel; col = o + 6; }
+        else if (lane >= 12 && lane < 15) { v = gs[(cfg.goal_is_cart ? DWBC_GS_CURR_CART : DWBC_GS_CURR_SPH) + lane - 12]; col = o + 7 + lane - 12; }
+        else if (lane >= 15 && lane < 18) { v = gs[DWBC_GS_DELTA_ORN + lane - 15]; col = o + 10 + lane - 15; }
+        else if (lane >= 24 && lane < 30) ds[DWBC_DS_LAST_ROOT_VEL + lane - 24] = sm[Ly::o_root + e * 26 + 7 + lane - 24];   // WG:908-910
+      }
+      if (col >= 0) { prop[col] = v; bad = bad || !(fabsf(v) <= c); }
+    }
+    if (__any_sync(FULL, bad) && lane == 0) oob_s[e] = 1;
+  };
+
+  // ---- 6. scalar pass: thread per env (warp 0); warps 1..6 assemble the simulator-only observation columns meanwhile ----
+  if (wid >= 1 && wid < V2_CW) {
+    for (int e = wid - 1; e < V2_E; e += V2_CW - 1) assemble(e, 0);
+  }
   if (tid < V2_E) {
     const int e = tid, env = e0 + e;
     float* root = sm + Ly::o_root + e * 26;
@@ -656,53 +714,14 @@ env_step_v2_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant
   cbar();
   V2_TICK(4);
 
-  // ---- 8. assembly pass: warp per env, lane per observation column (WG:966-1001, Appendix B) ----------
-  {
-    for (int e = wid; e < V2_E; e += V2_CW) {
-      const float* dof = sm + Ly::o_dof + e * 2 * ND;
-      const float* gs = sm + Ly::o_gs + e * DWBC_GS;
-      float* ds = sm + Ly::o_ds + e * DWBC_DS;
-      float* prop = sm + Ly::o_prop + e * P;
-      float* priv = sm + Ly::o_priv + e * NPRIV;
-      bool bad = false;
-      if (lane < ND) {            // dof position / velocity columns, last_dof_vel
-        const int d = ig2r_s[lane];
-        float pos = dof[2 * d];
-        if (d == cfg.waist_dof) pos = wrap_pi(pos);
-        const float v0 = (pos - defpos_s[d]) * cfg.obs_scale_dof_pos, v1 = dof[2 * d + 1] * cfg.obs_scale_dof_vel;
-        prop[5 + lane] = v0;
-        prop[5 + ND + lane] = v1;
-        bad = !(fabsf(v0) <= c) || !(fabsf(v1) <= c);
-        ds[DWBC_DS_LAST_DOF_VEL + lane] = dof[2 * lane + 1];
-      }
-      if (lane < NA) {            // last applied action column, last_actions, motor strength
-        const float v = sm[Ly::o_ah + e * AH * NA + (AH - 1) * NA + ig2r_s[lane]];
-        prop[5 + 2 * ND + lane] = v;
-        bad = bad || !(fabsf(v) <= c);
-        ds[DWBC_DS_LAST_ACTIONS + lane] = sm[Ly::o_act + e * NA + lane];
-        priv[6 + lane] = sm[Ly::o_motor + e * NA + lane] - 1.0f;
-      }
-      {
-        constexpr int o = 5 + 2 * ND + NA;
-        float v = 0.0f;
-        int col = -1;
-        if (lane < 4) {           // foot contacts (WG:1090-1098)
-          const float* f = sm + Ly::o_fs + e * 24 + 6 * (lane == 0 ? cfg.feet_perm[0] : (lane == 1 ? cfg.feet_perm[1] : (lane == 2 ? cfg.feet_perm[2] : cfg.feet_perm[3])));
-          float nrm = nsqrt(((((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]) + f[3] * f[3]) + f[4] * f[4]) + f[5] * f[5]);
-          v = nrm > 1.5f ? 1.0f : 0.0f; col = o + lane;
-        } else if (lane < 6) { v = sm[Ly::o_rp + 4 * e + lane - 4]; col = lane - 4; }
-        else if (lane < 9) { v = ds[DWBC_DS_BASE_ANG_VEL + lane - 6] * cfg.obs_scale_ang_vel; col = 2 + lane - 6; }
-        else if (lane < 11) { v = gs[lane - 9] * cfg.obs_scale_lin_vel; col = o + 4 + lane - 9; }
-        else if (lane == 11) { v = gs[2] * cfg.obs_scale_ang_vel; col = o + 6; }
-        else if (lane < 15) { v = gs[(cfg.goal_is_cart ? DWBC_GS_CURR_CART : DWBC_GS_CURR_SPH) + lane - 12]; col = o + 7 + lane - 12; }
-        else if (lane < 18) { v = gs[DWBC_GS_DELTA_ORN + lane - 15]; col = o + 10 + lane - 15; }
-        else if (lane < 23) priv[lane - 18] = sm[Ly::o_mass + e * 5 + lane - 18];
-        else if (lane == 23) priv[5] = sm[Ly::o_fric + e];
-        else if (lane < 30) ds[DWBC_DS_LAST_ROOT_VEL + lane - 24] = sm[Ly::o_root + e * 26 + 7 + lane - 24];   // WG:908-910
-        if (col >= 0) { prop[col] = v; bad = bad || !(fabsf(v) <= c); }
-      }
-      if (__any_sync(FULL, bad) && lane == 0) oob_s[e] = 1;
+  // ---- 8. assembly pass, second half: a reset env is re-assembled from its post-reset state first -------------
+  for (int e = wid; e < V2_E; e += V2_CW) {
+    if (flags_s[e] & F_RESET) {
+      if (lane == 0) oob_s[e] = 0;
+      __syncwarp();
+      assemble(e, 0);
     }
+    assemble(e, 1);
   }
   cbar();
   if (tid < V2_E) {

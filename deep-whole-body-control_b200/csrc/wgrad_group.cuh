@@ -8,6 +8,8 @@
 // Operand tiles, the SWIZZLE_128B_BASE32B MN-major layout, the 8-warp cp.async fill with asynchronous barrier arrival, the
 // bias-gradient column sums and the staged vector-reduction epilogue are those of gemm_tc2.cuh (weight-gradient branch).
 #pragma once
+#include <stdlib.h>
+
 #include "gemm_tc2.cuh"
 
 namespace dwbc {
@@ -195,7 +197,9 @@ inline int launch_wgrad_group(WGroup& g, int rows, cudaStream_t st) {
   }
   g.rows = rows;
   // slab length: ~4 work items per CTA, at least 4 chunks so that the epilogue stays amortised
-  int64_t total_items = (int64_t)4 * sms;
+  static int per_cta = 0;                              // work items per CTA (tuning knob: DWBC_WG_ITEMS)
+  if (!per_cta) { const char* e = getenv("DWBC_WG_ITEMS"); per_cta = e ? atoi(e) : 4; if (per_cta < 1) per_cta = 4; }
+  int64_t total_items = (int64_t)per_cta * sms;
   int64_t nslab = (total_items + g.n - 1) / g.n;
   int64_t slab = (rows + nslab - 1) / nslab;
   slab = (slab + T2_WCH - 1) / T2_WCH * T2_WCH;
