@@ -106,6 +106,11 @@ class Storage(C.Structure):
                 ("advantages", vp), ("log_prob", vp), ("hist_latent", vp), ("hist_latent_ld", i64)]
 
 
+class PdCfg(C.Structure):
+    _fields_ = [("n_dof", i32), ("n_act", i32), ("wrap_dof", i32)] + \
+               [(k, C.c_float * MAX_DOF) for k in ("p_gains", "d_gains", "action_scale", "default_dof_pos", "torque_limits")]
+
+
 class DwbcError(RuntimeError):
     pass
 
@@ -124,6 +129,7 @@ _SIGS = {
     "dwbc_policy_act": [vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp],
     "dwbc_critic_values": [vp, vp, vp, i64, vp, i32, vp, vp],
     "dwbc_hist_latent": [vp, vp, vp, i64, vp, i64, i32, vp, vp],
+    "dwbc_compute_torques": [vp, vp, vp, vp, vp, i32, vp],
     "dwbc_ppo_minibatch_grad": [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "dwbc_dagger_minibatch_grad": [vp, vp, vp, vp, i32, vp, vp, vp, vp],
     "dwbc_clip_adam_step": [vp, vp, vp, vp, i64, i64, vp, i32, vp, vp, vp],

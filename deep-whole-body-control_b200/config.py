@@ -79,6 +79,14 @@ def _f32(x):
     return float(np.float32(x))
 
 
+def _gains(table, dof_names, n_act):
+    """WG:648-658: gain of the first key of cfg.control.stiffness / damping contained in the DOF name, 0 if none."""
+    out = []
+    for name in list(dof_names)[:n_act]:
+        out.append(next((float(v) for k, v in table.items() if k in name), 0.0))
+    return out
+
+
 @dataclass
 class WidowGo1Params:
     # ---- dimensions (WGC:117-125; n_bodies/gripper_idx are URDF-derived, WG:287,318) ----
@@ -128,6 +136,10 @@ class WidowGo1Params:
          [-1.745, 2.147], [-3.14158, 3.14158], [0.015, 0.037], [-0.037, -0.015]])
     dof_vel_limits: List[float] = field(default_factory=lambda: [30.1, 30.1, 20.06] * 4 +
                                         [3.14] * 6 + [1.0, 1.0])
+    # PD controller of step() (WGC:166-170; p/d gains by DOF-name match WG:648-658): legs 50 / 1, arm 5 / 0.5
+    p_gains: List[float] = field(default_factory=lambda: [50.0] * 12 + [5.0] * 6)
+    d_gains: List[float] = field(default_factory=lambda: [1.0] * 12 + [0.5] * 6)
+    action_scale: List[float] = field(default_factory=lambda: [0.4, 0.45, 0.45] * 4 + [2.1, 0.6, 0.6, 0.0, 0.0, 0.0])
     torque_limits: List[float] = field(default_factory=lambda: [23.7, 23.7, 35.55] * 4 +
                                        [10, 20, 15, 2, 5, 1, 0, 0])
     soft_dof_vel_limit: float = 1.0     # WGC:276
@@ -293,6 +305,8 @@ class WidowGo1Params:
             clip_observations=cfg.normalization.clip_observations,
             observe_priv=cfg.domain_rand.observe_priv,
             default_dof_pos=[float(x) for x in default_dof_pos],
+            p_gains=_gains(cfg.control.stiffness, dof_names, cfg.env.num_actions), d_gains=_gains(cfg.control.damping, dof_names, cfg.env.num_actions),
+            action_scale=[float(x) for x in cfg.control.action_scale],
             base_init_state=[float(x) for x in base_init_state],
             origin_perturb_range=t.origin_perturb_range, init_vel_perturb_range=t.init_vel_perturb_range,
             box_env_origins_x=cfg.box.box_env_origins_x, box_env_origins_z=cfg.box.box_env_origins_z,

@@ -664,3 +664,32 @@ extern "C" int dwbc_pre_physics_actions(const float* policy_actions, const int32
   DWBC_LAUNCH_CHECK();
   return DWBC_OK;
 }
+
+// ---- PD torque controller (WG:1262-1295), SURVEY 8f row f1 ------------------------------------------------------------
+__global__ void compute_torques_kernel(const DwbcPdCfg cfg, const float* __restrict__ actions, const float* __restrict__ dof_state,
+                                       const float* __restrict__ motor_strength, float* __restrict__ torques, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * cfg.n_dof) return;
+  const int e = i / cfg.n_dof, j = i - e * cfg.n_dof;
+  float t = 0.0f;                                                          // gripper_torques_zero (WG:1291)
+  if (j < cfg.n_act) {
+    const float a = actions[(size_t)e * cfg.n_act + j];
+    const float scaled = (a * motor_strength[(size_t)e * cfg.n_act + j]) * cfg.action_scale[j];   // WG:1276
+    float q = dof_state[((size_t)e * cfg.n_dof + j) * 2];
+    if (j == cfg.wrap_dof) q = wrap_pi(q);                                 // WG:1278-1279
+    const float qd = dof_state[((size_t)e * cfg.n_dof + j) * 2 + 1];
+    t = cfg.p_gains[j] * ((scaled + cfg.default_dof_pos[j]) - q) - cfg.d_gains[j] * qd;           // WG:1281
+  }
+  const float lim = cfg.torque_limits[j];
+  torques[i] = fminf(fmaxf(t, -lim), lim);                                 // WG:1295
+}
+
+extern "C" int dwbc_compute_torques(const DwbcPdCfg* cfg, const float* actions, const float* dof_state, const float* motor_strength,
+                                    float* torques, int32_t num_envs, dwbc_stream_t stream) {
+  if (!cfg || !actions || !dof_state || !motor_strength || !torques || num_envs <= 0) return DWBC_ERR_ARG;
+  if (cfg->n_dof <= 0 || cfg->n_dof > DWBC_MAX_DOF || cfg->n_act <= 0 || cfg->n_act > cfg->n_dof || cfg->wrap_dof >= cfg->n_act) return DWBC_ERR_ARG;
+  const int total = num_envs * cfg->n_dof;
+  compute_torques_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*cfg, actions, dof_state, motor_strength, torques, num_envs);
+  DWBC_LAUNCH_CHECK();
+  return DWBC_OK;
+}

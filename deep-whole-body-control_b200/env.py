@@ -140,6 +140,7 @@ class FusedWidowGo1Core:
         self.episode_sums = {k: self._sums[:, i] for i, k in enumerate(self.sum_names)}
         self.episode_metric_sums = {k: self._sums[:, len(self.sum_names) + i] for i, k in enumerate(METRIC_NAMES)}
         self._stats = z(1 + self._sums_stride)
+        self._pd = None
         # --- terrain ---
         self.height_samples = None
         npts = p.num_height_points
@@ -305,6 +306,24 @@ class FusedWidowGo1Core:
                                                    p.action_hist_len, 1,
                                                    L.stream_ptr()), "dwbc_pre_physics_actions")
         return self.actions
+
+    def compute_torques(self, actions: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """WG:1262-1295 `_compute_torques` (PD controller; the reference calls it `decimation` times per policy step, WG:1175-1183,
+        with the dof state refreshed in between).  Writes `self.torques` [N, n_dof] and returns it."""
+        p = self.p
+        if self._pd is None:
+            pd = L.PdCfg()
+            pd.n_dof, pd.n_act, pd.wrap_dof = p.num_dofs, p.num_actions, p.num_actions - 8     # column -8 of the 18-wide tensor (WG:1279)
+            for k, src in (("p_gains", p.p_gains), ("d_gains", p.d_gains), ("action_scale", p.action_scale),
+                           ("default_dof_pos", p.default_dof_pos), ("torque_limits", p.torque_limits)):
+                arr = getattr(pd, k)
+                for i, v in enumerate(src):
+                    arr[i] = float(v)
+            self._pd = pd
+        a = self.actions if actions is None else actions.contiguous()
+        L.check(self._lib.dwbc_compute_torques(C.addressof(self._pd), L.ptr(a), L.ptr(self.dof_state), L.ptr(self.motor_strength),
+                                               L.ptr(self.torques), p.num_envs, L.stream_ptr()), "dwbc_compute_torques")
+        return self.torques
 
     def post_physics_step(self, rand: Optional[torch.Tensor] = None):
         """WG:865-915 after the gym.refresh_* calls.  `rand` ([N, RAND_COLS] uniforms) selects table

@@ -247,6 +247,19 @@ typedef struct DwbcNetCfg {
   int64_t off_carm_w[DWBC_MAX_LAYERS + 1], off_carm_b[DWBC_MAX_LAYERS + 1];
 } DwbcNetCfg;
 
+/* PD torque controller of step() (WG:1262-1295 `_compute_torques`, called `decimation` times per policy step, WG:1175-1183):
+ *   tau[:, j] = clip(p_j * (a_j * motor_strength_j * action_scale_j + default_j - q_j) - d_j * qdot_j, +-limit_j)   j < n_act
+ *   tau[:, j] = 0                                                                                                n_act <= j < n_dof
+ * `actions` are the delayed actions in Isaac Gym order (output of dwbc_pre_physics_actions).  The reference wraps column -8 of
+ * the n_act-wide position tensor to (-pi, pi] (WG:1279) -- i.e. DOF n_act-8, which is not the waist; `wrap_dof` restates it as
+ * written (-1: no wrap). */
+typedef struct DwbcPdCfg {
+  int32_t n_dof, n_act, wrap_dof;
+  float p_gains[DWBC_MAX_DOF], d_gains[DWBC_MAX_DOF], action_scale[DWBC_MAX_DOF], default_dof_pos[DWBC_MAX_DOF], torque_limits[DWBC_MAX_DOF];
+} DwbcPdCfg;
+int dwbc_compute_torques(const DwbcPdCfg* cfg, const float* actions, const float* dof_state, const float* motor_strength,
+                         float* torques, int32_t num_envs, dwbc_stream_t stream);
+
 /* Bytes of device workspace the forward / update entry points need for `rows` rows. */
 int64_t dwbc_workspace_bytes(const DwbcNetCfg* net, int64_t rows);
 

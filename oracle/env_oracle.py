@@ -465,3 +465,19 @@ class EnvOracle:
 def heights_obs(root_z, measured_heights, scale):
     """Perceptive obs formula of the base class (LR:221-223)."""
     return torch.clip(root_z.unsqueeze(1) - 0.5 - measured_heights, -1, 1.0) * scale
+
+
+def compute_torques(actions, dof_pos, dof_vel, motor_strength, p_gains, d_gains, action_scale, default_dof_pos, torque_limits, wrap_col=-8):
+    """`WidowGo1._compute_torques` (WG:1262-1295) with adaptive_arm_gains = torque_supervision = False (WGC:168,173).
+
+    actions / motor_strength [N, n_act] (delayed actions, Isaac Gym order), dof_pos / dof_vel [N, n_dof], gains / scale [n_act],
+    default_dof_pos / torque_limits [n_dof].  Returns torques [N, n_dof] (zero for the non-driven gripper DOFs, WG:1291).
+    The reference wraps column -8 of the n_act-wide position tensor (WG:1279); that is DOF n_act-8, restated as written."""
+    from .torch_utils import torch_wrap_to_pi_minuspi
+    n_act = actions.shape[1]
+    scaled = actions * motor_strength * action_scale                                        # WG:1276
+    q = dof_pos[:, :n_act].clone()                                                          # WG:1278
+    q[:, wrap_col] = torch_wrap_to_pi_minuspi(q[:, wrap_col])                               # WG:1279
+    tau = p_gains * (scaled + default_dof_pos[:n_act] - q) - d_gains * dof_vel[:, :n_act]   # WG:1281
+    tau = torch.cat([tau, torch.zeros(actions.shape[0], dof_pos.shape[1] - n_act)], dim=-1)  # WG:1291
+    return torch.clip(tau, -torque_limits, torque_limits)                                   # WG:1295

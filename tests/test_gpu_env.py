@@ -150,3 +150,23 @@ def test_obs_written_directly_into_storage_row_and_structure():
         assert torch.equal(h[~fill][:, :-1], prev_hist[~fill][:, 1:])
         assert torch.equal(h[fill], prop[fill][:, None, :].expand(-1, p.history_len, -1))
         assert float(obs.abs().max()) <= 100.0
+
+
+@pytest.mark.gpu
+def test_torque_controller_matches_reference_golden():
+    """dwbc_compute_torques (WG:1262-1295) against the golden vectors of the unmodified reference: exact fp32 arithmetic (the kernel is
+    built without FMA contraction); the one wrapped column may differ by an ulp of the angle times p_gain (stated tolerance 5e-5)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "torques.npz"))
+    N = int(g["meta"][0])
+    p = E.make_params("flat", N)
+    from dwbc_b200.env import FusedWidowGo1Core
+    env = FusedWidowGo1Core(p, "cuda:0", state=E.initial(p, 3))
+    ds = torch.stack([torch.from_numpy(g["dof_pos"]), torch.from_numpy(g["dof_vel"])], dim=-1).reshape(N * p.num_dofs, 2)
+    env.dof_state.copy_(ds.cuda())
+    env.motor_strength.copy_(torch.from_numpy(g["motor"]).cuda())
+    out = env.compute_torques(torch.from_numpy(g["actions"]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(out, g["torques"], rtol=0, atol=5e-5)
+    wrap = p.num_actions - 8
+    cols = [j for j in range(p.num_dofs) if j != wrap]
+    np.testing.assert_array_equal(out[:, cols], g["torques"][:, cols])

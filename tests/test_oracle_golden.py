@@ -117,3 +117,16 @@ def test_ppo_oracle_matches_reference_golden():
     assert abs(float(torch.stack([l["surrogate"] for l in logs]).mean()) - res[1]) < 1e-5
     assert abs(float(torch.stack([l["priv_reg"] for l in logs]).mean()) - res[5]) < 1e-5
     assert logs[0]["mixing_ratio"] == res[3] and logs[0]["priv_reg_coef"] == res[6]
+
+
+def test_torque_controller_oracle_matches_reference_golden():
+    """`_compute_torques` (WG:1262-1295) restatement against the unmodified reference method (tests/golden/make_golden_torques.py)."""
+    from dwbc_b200.config import WidowGo1Params
+    from oracle import env_oracle as EO
+    g = np.load(os.path.join(G, "torques.npz"))
+    p = WidowGo1Params(num_envs=int(g["meta"][0]))
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    out = EO.compute_torques(t("actions"), t("dof_pos"), t("dof_vel"), t("motor"), torch.tensor(p.p_gains), torch.tensor(p.d_gains),
+                             torch.tensor(p.action_scale), torch.tensor(p.default_dof_pos), torch.tensor(p.torque_limits))
+    np.testing.assert_array_equal(out.numpy(), g["torques"])
+    assert np.all(g["torques"][:, p.num_actions:] == 0.0)
