@@ -1,0 +1,107 @@
+"""Host-side logic of the reference mirror that needs no GPU: schedules, checkpoint layout, storage bookkeeping."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import dwbc_b200  # noqa: E402,F401
+from dwbc_b200.actor_critic import FlatActorCritic  # noqa: E402
+from dwbc_b200.ppo import FusedPPO  # noqa: E402
+from oracle import ppo_oracle as PO  # noqa: E402
+from test_oracle_golden import G, golden_params, ppo_hp  # noqa: E402
+
+
+def make_cpu_alg(**over):
+    ac = FlatActorCritic(device="cpu", num_priv=24, num_hist=10, num_prop=76)
+    hp = ppo_hp()
+    hp.update(over)
+    return FusedPPO(ac, device="cpu", **hp)
+
+
+def test_schedules_match_reference_formulas():
+    """PPO:178-179 (priv_reg_coef) and PPO:301-302 (value mixing ratio) as restated by the oracle, over the whole counter range."""
+    alg = make_cpu_alg(mixing_schedule=[0.5, 2000, 4000], priv_reg_coef_schedual=[0, 0.1, 3000, 7000])
+    for c in (0, 1, 1999, 2000, 2001, 3000, 4000, 5999, 6000, 6500, 10000, 20000):
+        alg.counter = c
+        assert alg.get_value_mixing_ratio() == PO.value_mixing_ratio(c, [0.5, 2000, 4000])
+        assert alg.get_priv_reg_coef() == PO.priv_reg_coef(c, [0, 0.1, 3000, 7000])
+
+
+def test_unsupported_reference_switches_fail_loudly():
+    from dwbc_b200 import _lib as L
+    with pytest.raises(L.DwbcError):
+        make_cpu_alg(torque_supervision=True)
+    with pytest.raises(L.DwbcError):
+        make_cpu_alg(adaptive_arm_gains=True)
+    with pytest.raises(L.DwbcError):
+        make_cpu_alg(schedule="adaptive")
+
+
+def test_checkpoint_round_trip_keeps_reference_names_and_shapes():
+    """OPR:276-290: model_state_dict / optimizer_state_dict.  Names and order are the reference ActorCritic's (pinned by the golden file)."""
+    g = np.load(os.path.join(G, "ppo.npz"))
+    P = golden_params(g, int(g["meta"][2]))
+    alg = make_cpu_alg()
+    ac = alg.actor_critic
+    ac.load_state_dict(P)
+    sd = ac.state_dict()
+    assert list(sd.keys()) == list(g["names"]) and list(sd.keys())[0] == "std"
+    for k in P:
+        assert sd[k].shape == P[k].shape and torch.equal(sd[k], P[k])
+    assert sum(v.numel() for v in sd.values()) == 168698 and ac.num_params == ac.flat.numel() == 168928      # padded flat length
+    # padded flat buffer: every tensor starts on a 32-float boundary, pads stay zero
+    for n, off in ac.offsets.items():
+        assert off % 32 == 0
+    used = torch.zeros_like(ac.flat, dtype=torch.bool)
+    for n, v in ac.views.items():
+        used[ac.offsets[n]:ac.offsets[n] + v.numel()] = True
+    assert float(ac.flat[~used].abs().max()) == 0.0
+    # a second model loaded from the checkpoint is identical
+    ac2 = FlatActorCritic(device="cpu", num_priv=24, num_hist=10, num_prop=76)
+    ac2.load_state_dict(sd)
+    assert torch.equal(ac2.flat, ac.flat)
+    with pytest.raises(KeyError):
+        ac2.load_state_dict({k: v for k, v in list(sd.items())[1:]})
+    # optimizer: torch.optim.Adam layout (state[i] = {step, exp_avg, exp_avg_sq}, param_groups[0]['params'] = indices)
+    opt = alg.optimizer
+    assert opt.state_dict()["state"] == {}
+    opt.step = 3
+    opt.m.normal_()
+    opt.v.uniform_()
+    osd = opt.state_dict()
+    names = list(sd.keys())
+    assert sorted(osd["state"].keys()) == list(range(len(names))) and osd["param_groups"][0]["params"] == list(range(len(names)))
+    for i, n in enumerate(names):
+        st = osd["state"][i]
+        assert st["exp_avg"].shape == sd[n].shape and st["exp_avg_sq"].shape == sd[n].shape and float(st["step"]) == 3.0
+    alg2 = make_cpu_alg()
+    alg2.optimizer.load_state_dict(osd)
+    assert alg2.optimizer.step == 3
+    for n in names:
+        o, k = ac.offsets[n], sd[n].numel()
+        assert torch.equal(alg2.optimizer.m[o:o + k], opt.m[o:o + k]) and torch.equal(alg2.optimizer.v[o:o + k], opt.v[o:o + k])
+    assert osd["param_groups"][0]["lr"] == ppo_hp()["learning_rate"] and osd["param_groups"][0]["betas"] == (0.9, 0.999)
+
+
+def test_storage_shapes_follow_reference():
+    """RS:65-84 field names and shapes; observations are a view of the [T+1, N, n_obs] buffer the env kernel writes into."""
+    alg = make_cpu_alg()
+    alg.init_storage(8, 5, [860], [None], [18])
+    s = alg.storage
+    assert s.observations.shape == (5, 8, 860) and s.obs_row(5).shape == (8, 860)
+    assert s.observations.data_ptr() == s.obs_row(0).data_ptr()
+    for k, shp, dt in (("rewards", (5, 8, 2), torch.float32), ("actions", (5, 8, 18), torch.float32), ("dones", (5, 8, 1), torch.uint8),
+                       ("values", (5, 8, 2), torch.float32), ("returns", (5, 8, 2), torch.float32), ("advantages", (5, 8, 2), torch.float32),
+                       ("actions_log_prob", (5, 8, 2), torch.float32), ("mu", (5, 8, 18), torch.float32), ("sigma", (5, 8, 18), torch.float32)):
+        t = getattr(s, k)
+        assert tuple(t.shape) == shp and t.dtype == dt, k
+    idx, mbs = s.draw_indices(4)
+    assert mbs == 10 and sorted(idx.tolist()) == list(range(40))
+    batches = list(s.mini_batch_generator(4, 3, idx))
+    assert len(batches) == 12 and all(b.numel() == 10 for b in batches) and torch.equal(batches[0], batches[4])     # RS:182-188 order
