@@ -170,3 +170,12 @@ def test_torque_controller_matches_reference_golden():
     wrap = p.num_actions - 8
     cols = [j for j in range(p.num_dofs) if j != wrap]
     np.testing.assert_array_equal(out[:, cols], g["torques"][:, cols])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["flat", "full"])
+def test_general_fallback_kernel_matches_reference_golden(name, monkeypatch):
+    """`env_step_kernel` (warp per env; any N / n_dof / unaligned buffers) is what runs when the 32-envs-per-CTA TMA kernel does not
+    apply; DWBC_ENV_KERNEL_V1 forces it on the golden case."""
+    monkeypatch.setenv("DWBC_ENV_KERNEL_V1", "1")
+    test_env_step_matches_reference_golden(name)
