@@ -105,3 +105,29 @@ def test_storage_shapes_follow_reference():
     assert mbs == 10 and sorted(idx.tolist()) == list(range(40))
     batches = list(s.mini_batch_generator(4, 3, idx))
     assert len(batches) == 12 and all(b.numel() == 10 for b in batches) and torch.equal(batches[0], batches[4])     # RS:182-188 order
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/legged_gym"), reason="authoring container only: needs the reference's config module")
+def test_default_params_equal_the_reference_config():
+    """`WidowGo1Params()` hard-codes the widowGo1 constants so that the kernels can run without legged_gym; this pins every one of them
+    (dims, ranges, thresholds, curricula, PD gains, action scale, active reward terms and scales) to `WidowGo1RoughCfg` as shipped, read
+    through `WidowGo1Params.from_legged_gym` (the path a real integration takes).  URDF-derived inputs are passed through."""
+    import dataclasses
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_harness as RH
+    from dwbc_b200.config import DOF_NAMES_IG, WidowGo1Params
+    _, Cfg, _ = RH.import_reference_env()
+    cfg = Cfg()
+    d = WidowGo1Params()
+    scales = lambda o: {k: getattr(o, k) for k in dir(o) if not k.startswith("_")}  # noqa: E731  (class_to_dict of legged_gym/utils/helpers.py)
+    p = WidowGo1Params.from_legged_gym(
+        cfg, num_envs=d.num_envs, dt=cfg.control.decimation * cfg.sim.dt, dof_names=DOF_NAMES_IG, num_bodies=d.num_bodies, gripper_idx=d.gripper_idx,
+        feet_indices=d.feet_indices, penalized_contact_indices=d.penalized_contact_indices, termination_contact_indices=d.termination_contact_indices,
+        dof_pos_limits=d.dof_pos_limits, dof_vel_limits=d.dof_vel_limits, torque_limits=d.torque_limits, default_dof_pos=d.default_dof_pos,
+        base_init_state=d.base_init_state, reward_scales=scales(cfg.rewards.scales), arm_reward_scales=scales(cfg.rewards.arm_scales))
+    nz = lambda t: {k: v for k, v in t.items() if v != 0}  # noqa: E731  (zero-scale terms are dropped, WG:130-136)
+    for f in dataclasses.fields(d):
+        a, b = getattr(d, f.name), getattr(p, f.name)
+        if f.name in ("reward_scales", "arm_reward_scales"):
+            a, b = nz(a), nz(b)
+        assert a == b, (f.name, a, b)
