@@ -17,9 +17,9 @@ ENV_CONFIGS = {
     # default widowGo1 flat config (BASELINE.json configs[1] semantics)
     "flat": dict(),
     # every optional branch: extra reward terms on both channels, termination terms, contact
-    # termination, positive-reward clip off, height scan on
+    # termination, positive-reward clip off, height scan on, terrain curriculum on (LR:421-441)
     "full": dict(
-        measure_heights=True, tot_rows=400, tot_cols=600, termination_contact_indices=[2],
+        measure_heights=True, tot_rows=400, tot_cols=600, termination_contact_indices=[2], terrain_curriculum=True,
         reward_scales={
             "action_rate": -0.01, "ang_vel_xy": -0.05, "base_height": -1.0, "collision": -1.0, "dof_acc": -2.5e-7,
             "dof_pos_limits": -10.0, "dof_vel": -1e-3, "dof_vel_limits": -0.1, "energy_square": -6e-5,
@@ -55,6 +55,17 @@ def initial(p, seed):
     if p.measure_heights:
         st["height_samples"] = synth.height_field(p, seed)
     return st
+
+
+def sim_state(p, seed, t, env_origins=None, **kw):
+    """synth.sim_state, with the robot placed RELATIVE to its current env origin when the terrain curriculum is on
+    (LR:430 measures the distance walked from the origin: absolute +-5 m positions would make every reset a promotion).
+    `env_origins` = the [N,3] origins before the step (numpy / tensor), i.e. state the caller carries."""
+    sim = synth.sim_state(p, seed, t, **kw)
+    if p.terrain_curriculum and env_origins is not None:
+        org = env_origins.detach().cpu().numpy() if isinstance(env_origins, torch.Tensor) else np.asarray(env_origins)
+        sim["root_states"][:, 0, 0:2] += org[:, 0:2].astype(np.float32)
+    return sim
 
 
 def oracle_state(p, st):

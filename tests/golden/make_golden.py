@@ -25,7 +25,7 @@ import ref_harness as H  # noqa: E402
 import envstate as E  # noqa: E402
 from dwbc_b200 import synth  # noqa: E402
 from oracle import ppo_oracle as PO  # noqa: E402
-from oracle.env_oracle import EnvOracle  # noqa: E402
+from oracle.env_oracle import EnvOracle, heights_obs as EO_heights_obs  # noqa: E402
 
 ENV_N, ENV_STEPS, ENV_SEED, ENV_COUNTER0 = 48, 20, 3, 143
 PPO_N, PPO_T, PPO_SEED, PPO_COUNTER = 64, 40, 7, 1500
@@ -38,6 +38,18 @@ def _close(a, b, tol, what):
     return d
 
 
+def _ref_heights_obs(ref):
+    """Perceptive observation columns of the BASE class (LR:205-226; WidowGo1.compute_observations, WG:966-1001, does not append
+    them): run LeggedRobot.compute_observations on the reference object and keep the last 187 columns."""
+    from legged_gym.envs.base.legged_robot import LeggedRobot
+    keep = ref.obs_buf
+    ref.projected_gravity, ref.add_noise = torch.zeros(ref.num_envs, 3), False
+    LeggedRobot.compute_observations(ref)
+    h = ref.obs_buf[:, -ref.measured_heights.shape[1]:].clone()
+    ref.obs_buf = keep
+    return h
+
+
 def gen_env(name):
     p = E.make_params(name, ENV_N)
     st = E.initial(p, ENV_SEED)
@@ -47,10 +59,12 @@ def gen_env(name):
     ref.update_command_curriculum()
     ref.common_step_counter = orc.common_step_counter = ENV_COUNTER0
     out = {k: [] for k in ("obs100", "rew", "arm_rew", "reset", "time_out", "commands", "ee_goal_sphere",
-                           "goal_timer", "ep_len", "heights", "ep_stats")}
+                           "goal_timer", "ep_len", "heights", "ep_stats", "env_origins_pre", "env_origins", "terrain_levels",
+                           "heights_obs")}
     worst = 0.0
     for t in range(1, ENV_STEPS + 1):
-        sim = synth.sim_state(p, ENV_SEED, t)
+        out["env_origins_pre"].append(ref.env_origins.numpy().copy())
+        sim = E.sim_state(p, ENV_SEED, t, ref.env_origins)
         H.load_sim_into_reference(ref, p, sim)
         E.load_sim_into_oracle(orc, p, sim)
         tab = torch.from_numpy(synth.rand_table(p, ENV_SEED, t))
@@ -76,6 +90,10 @@ def gen_env(name):
         pairs += [(ref.episode_metric_sums[k], orc.s.episode_metric_sums[k], "metric_" + k) for k in ref.episode_metric_sums]
         if p.measure_heights:
             pairs.append((ref.measured_heights, orc.measured_heights, "heights"))
+            ref_ho = _ref_heights_obs(ref)                                   # LR:221-223 executed by the base class itself
+            pairs.append((ref_ho, EO_heights_obs(orc.root[:, 2], orc.measured_heights, p.obs_scale_height), "heights_obs"))
+        if p.terrain_curriculum:
+            pairs += [(ref.terrain_levels, orc.s.terrain_levels, "terrain_levels"), (ref.env_origins, orc.s.env_origins, "env_origins")]
         stats = []
         if int(rst.sum()):
             for k in [k for k in ref.extras["episode"] if not k.startswith("coeff")]:
@@ -92,6 +110,9 @@ def gen_env(name):
         out["goal_timer"].append(ref.goal_timer.numpy().copy())
         out["ep_len"].append(ref.episode_length_buf.numpy().copy())
         out["heights"].append(ref.measured_heights.numpy().copy() if p.measure_heights else np.zeros((0,), np.float32))
+        out["heights_obs"].append(ref_ho.numpy().copy() if p.measure_heights else np.zeros((0,), np.float32))
+        out["env_origins"].append(ref.env_origins.numpy().copy())
+        out["terrain_levels"].append(ref.terrain_levels.numpy().copy() if p.terrain_curriculum else np.zeros((0,), np.int64))
         out["ep_stats"].append(np.array(stats if stats else [np.nan] * (len(ref.episode_sums) + len(ref.episode_metric_sums)),
                                         np.float32))
     arrs = {k: np.stack(v) for k, v in out.items()}
@@ -103,8 +124,13 @@ def gen_env(name):
                 stat_names=np.array([k for k in ref.extras["episode"] if not k.startswith("coeff")]),
                 meta=np.array([ENV_N, ENV_STEPS, ENV_SEED, ENV_COUNTER0]))
     np.savez_compressed(os.path.join(HERE, f"env_{name}.npz"), **arrs)
+    extra = ""
+    if p.terrain_curriculum:
+        lv = arrs["terrain_levels"]
+        d = np.diff(np.concatenate([np.asarray(st["terrain_levels"])[None], lv]), axis=0)
+        extra = f"; terrain levels: {int((d > 0).sum())} promotions, {int((d < 0).sum())} demotions / wraps, final range {lv[-1].min()}..{lv[-1].max()}"
     print(f"env_{name}: oracle == reference (max diff {worst}) over {ENV_STEPS} steps; resets/step "
-          f"{arrs['reset'].sum(1).tolist()}, timeouts {int(arrs['time_out'].sum())}")
+          f"{arrs['reset'].sum(1).tolist()}, timeouts {int(arrs['time_out'].sum())}{extra}")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -83,7 +83,7 @@ def make_reference_env(p, st, seed, overrides=None):
             setattr(obj, k, v)
     cfg.rewards.only_positive_rewards = p.only_positive_rewards
     cfg.terrain.measure_heights = p.measure_heights
-    cfg.terrain.curriculum = False
+    cfg.terrain.curriculum = bool(p.terrain_curriculum)          # mesh_type stays 'trimesh' (WGC:290), so WG:115-116 keeps it
     e.cfg = cfg
     e.sim_params = SimpleNamespace(dt=0.005)
     e.num_envs, e.device, e.num_dofs, e.num_bodies, e.num_actions = N, "cpu", p.num_dofs, p.num_bodies, p.num_actions
@@ -158,10 +158,17 @@ def make_reference_env(p, st, seed, overrides=None):
     e.gym = _Gym()
     e.sim = None
     e.init_done = True
+    if p.measure_heights or p.terrain_curriculum:
+        e.terrain = SimpleNamespace(cfg=cfg.terrain, env_length=p.terrain_env_length)
     if p.measure_heights:
-        e.terrain = SimpleNamespace(cfg=cfg.terrain)
         e.height_samples = T(st["height_samples"])
         e.height_points = e._init_height_points()
+    if p.terrain_curriculum:
+        # base-class wiring of LR:717-731 (WidowGo1._get_env_origins, WG:207-228, does not create these tensors)
+        assert cfg.terrain.curriculum, "WG:115-116 switched the terrain curriculum off"
+        e.terrain_levels, e.terrain_types = T(st["terrain_levels"]), T(st["terrain_types"])
+        e.terrain_origins = T(st["terrain_origins"])
+        e.max_terrain_level = p.max_terrain_level
     e.measured_heights = 0
     e._prepare_reward_function()
 
@@ -201,6 +208,25 @@ def make_reference_env(p, st, seed, overrides=None):
     def pre_root(env_ids):
         rr.ids, rr.col = env_ids, C.RAND_RST_XY
 
+    if p.terrain_curriculum:
+        # LR:438 draws with torch.randint_like (not torch_rand_float): for the duration of the reference's own
+        # _update_terrain_curriculum the harness serves that draw from column RAND_TERRAIN of the step's table,
+        # floor(u * max_level) clamped to max_level - 1 (the integer the oracle and the kernel derive from the same uniform)
+        orig_tc = e._update_terrain_curriculum
+
+        def terrain_curriculum(env_ids):
+            real = torch.randint_like
+
+            def from_table(t, high, **kw):
+                r = (rr.table[env_ids, C.RAND_TERRAIN] * high).long().clamp(max=high - 1)
+                assert r.shape == t.shape
+                return r.to(t.dtype)
+            torch.randint_like = from_table
+            try:
+                return orig_tc(env_ids)
+            finally:
+                torch.randint_like = real
+        e._update_terrain_curriculum = terrain_curriculum
     wrap("_resample_ee_goal", pre_goal)
     wrap("_resample_ee_goal_orn_once", pre_orn)
     wrap("_resample_ee_goal_sphere_once", pre_sph)

@@ -41,9 +41,9 @@ def test_env_step_matches_reference_golden(name):
     core = make_core(p, E.initial(p, seed))
     core.common_step_counter = counter0
     for t in range(1, steps + 1):
-        load_sim(core, p, synth.sim_state(p, seed, t))
-        core.post_physics_step(torch.from_numpy(synth.rand_table(p, seed, t)).cuda())
         i = t - 1
+        load_sim(core, p, E.sim_state(p, seed, t, g["env_origins_pre"][i]))
+        core.post_physics_step(torch.from_numpy(synth.rand_table(p, seed, t)).cuda())
         np.testing.assert_array_equal(core.reset_buf.cpu().numpy(), g["reset"][i], err_msg=f"reset step {t}")
         np.testing.assert_array_equal(core.time_out_buf.cpu().numpy(), g["time_out"][i])
         np.testing.assert_array_equal(core.episode_length_buf.cpu().numpy(), g["ep_len"][i])
@@ -55,6 +55,10 @@ def test_env_step_matches_reference_golden(name):
         np.testing.assert_array_equal(core.goal_timer.cpu().numpy(), g["goal_timer"][i])
         if p.measure_heights:
             np.testing.assert_allclose(core.measured_heights.cpu().numpy(), g["heights"][i], rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(core.heights_obs.cpu().numpy(), g["heights_obs"][i], rtol=1e-6, atol=1e-6)   # LR:221-223
+        if p.terrain_curriculum:                                                          # LR:421-441
+            np.testing.assert_array_equal(core.terrain_levels.cpu().numpy(), g["terrain_levels"][i], err_msg=f"terrain level step {t}")
+            np.testing.assert_array_equal(core.env_origins.cpu().numpy(), g["env_origins"][i])
         if g["reset"][i].sum():
             ep = core.extras["episode"]
             got = np.array([float(ep[k]) for k in g["stat_names"]], np.float32)
@@ -83,7 +87,7 @@ def test_env_step_matches_oracle_full_size(name, N):
     core.common_step_counter = orc.common_step_counter = 146
     mism = 0
     for t in range(1, 7):
-        sim = synth.sim_state(p, seed, t)
+        sim = E.sim_state(p, seed, t, orc.s.env_origins)
         load_sim(core, p, sim)
         E.load_sim_into_oracle(orc, p, sim)
         tab = torch.from_numpy(synth.rand_table(p, seed, t))
@@ -103,7 +107,13 @@ def test_env_step_matches_oracle_full_size(name, N):
         np.testing.assert_allclose(core._root_states.cpu().numpy(), orc.s.root_states_full.numpy(), **FTOL)
         np.testing.assert_allclose(core.dof_state.cpu().numpy(), orc.s.dof_state.numpy(), **FTOL)
         np.testing.assert_array_equal(core.episode_length_buf.cpu().numpy(), orc.s.episode_length_buf.numpy())
-    assert orc.pushed or True
+        if p.measure_heights:
+            np.testing.assert_allclose(core.measured_heights.cpu().numpy(), orc.measured_heights.numpy(), rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(core.heights_obs.cpu().numpy(),
+                                       EO.heights_obs(orc.root[:, 2], orc.measured_heights, p.obs_scale_height).numpy(), rtol=1e-6, atol=1e-6)
+        if p.terrain_curriculum:
+            np.testing.assert_array_equal(core.terrain_levels.cpu().numpy(), orc.s.terrain_levels.numpy())
+            np.testing.assert_array_equal(core.env_origins.cpu().numpy(), orc.s.env_origins.numpy())
 
 
 def test_philox_mode_equals_table_mode():

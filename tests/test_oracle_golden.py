@@ -30,9 +30,10 @@ def test_env_oracle_matches_reference_golden(name):
     rt = E.runtime(p)
     assert list(g["sum_names"]) == p.sum_slots()
     for t in range(1, steps + 1):
-        E.load_sim_into_oracle(orc, p, synth.sim_state(p, seed, t))
-        obs, rew, arew, rst, ex = orc.post_physics_step(torch.from_numpy(synth.rand_table(p, seed, t)), rt)
         i = t - 1
+        np.testing.assert_array_equal(orc.s.env_origins.numpy(), g["env_origins_pre"][i])
+        E.load_sim_into_oracle(orc, p, E.sim_state(p, seed, t, g["env_origins_pre"][i]))
+        obs, rew, arew, rst, ex = orc.post_physics_step(torch.from_numpy(synth.rand_table(p, seed, t)), rt)
         np.testing.assert_array_equal(obs[:, :100].numpy(), g["obs100"][i])
         np.testing.assert_array_equal(rew.numpy(), g["rew"][i])
         np.testing.assert_array_equal(arew.numpy(), g["arm_rew"][i])
@@ -44,6 +45,10 @@ def test_env_oracle_matches_reference_golden(name):
         np.testing.assert_array_equal(orc.s.episode_length_buf.numpy(), g["ep_len"][i])
         if p.measure_heights:
             np.testing.assert_array_equal(orc.measured_heights.numpy(), g["heights"][i])
+            np.testing.assert_array_equal(EO.heights_obs(orc.root[:, 2], orc.measured_heights, p.obs_scale_height).numpy(), g["heights_obs"][i])
+        if p.terrain_curriculum:                                                          # LR:421-441 (row a21)
+            np.testing.assert_array_equal(orc.s.terrain_levels.numpy(), g["terrain_levels"][i])
+            np.testing.assert_array_equal(orc.s.env_origins.numpy(), g["env_origins"][i])
         if int(rst.sum()):
             got = np.array([float(ex["episode"][k]) for k in g["stat_names"]], np.float32)
             np.testing.assert_array_equal(got, g["ep_stats"][i])
@@ -53,6 +58,10 @@ def test_env_oracle_matches_reference_golden(name):
     np.testing.assert_array_equal(orc.s.dof_state.numpy(), g["final_dof"])
     np.testing.assert_array_equal(np.stack([orc.s.episode_sums[k].numpy() for k in g["sum_names"]]), g["final_sums"])
     assert g["reset"].sum() > 0 and g["time_out"].sum() > 0
+    if p.terrain_curriculum:      # the fixture really exercises promotions, demotions and the wrap of solved top levels
+        lv = np.concatenate([E.initial(p, seed)["terrain_levels"][None], g["terrain_levels"]])
+        d = np.diff(lv, axis=0)
+        assert (d > 0).sum() >= 20 and (d < 0).sum() >= 20 and (d < -1).sum() >= 1
 
 
 def ppo_hp():
