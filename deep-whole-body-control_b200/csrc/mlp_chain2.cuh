@@ -1,0 +1,695 @@
+// Fused layer chains of the ActorCritic (AC:86-353) on the tcgen05 tensor cores, second generation.
+//
+// What changed against the first chain kernel (round 1: one 128-row tile per CTA, strict MMA -> epilogue -> MMA):
+//   * TWO row tiles in flight per CTA (slots X and Y).  Each slot owns ONE operand tile in shared memory that every op
+//     updates in place, one accumulator in TMEM and (error-compensated mode) one TMEM region for the low parts of its
+//     operand.  The MMA thread issues  X.op_n, Y.op_n, X.op_n+1, ...  and the sixteen epilogue warps drain X.op_n while the
+//     tensor core works on Y.op_n: the serial chain of one tile is hidden behind the other tile.
+//   * Both slots run the same program, so one weight image per op serves two tiles (half the L2 traffic per tile).
+//   * The trunk a second head needs is re-read from the activation buffer the backward pass needs anyway (L2 hit) instead
+//     of occupying a second shared-memory tile -- that is what makes room for the second slot.
+//   * "3xTF32" (precision 2): x = hi + lo with hi = the 19 leading bits the tensor core reads (kind::tf32 TRUNCATES the
+//     13 low mantissa bits of a 32-bit operand -- measured, tools/probes/ts_probe.cu) and lo = x - hi (exact in fp32).
+//     D = A_hi W_hi + A_lo W_hi + A_hi W_lo: the first and third products read the fp32 tile / the raw and the "lo" weight
+//     image from shared memory, the second reads A_lo from TMEM (tcgen05.mma with the A operand in tensor memory), written
+//     there by the epilogue that produced A.  The dropped A_lo W_lo term is 2^-22 relative: fp32-grade results.
+//   * The heads' epilogues finish the job (north_star: "log-prob, ratio/clip/min and entropy fused into the epilogue"):
+//     rollout: action sampling + two-channel Gaussian log-prob (AC:326-345); update: PPO surrogate / clipped value loss /
+//     entropy / privileged-latent regulariser and their gradients w.r.t. the network outputs (PPO:166-221).
+//   * Work items (program, tile pair) are handed out through an atomic queue (longest program first).
+//
+// Tile geometry (unchanged): [128 rows x 128 k] fp32, element (r, k) at float ((r/8)*32 + k/4)*32 + (r%8)*4 + k%4
+// (8-row x 16-byte core matrices, LBO = 128 B, SBO = 4096 B).  TMEM: slot s owns columns [256 s, 256 s + 256):
+// accumulator D at +0 (lane = row, column = output feature), A_lo at +128 (lane = row, column = k).
+#pragma once
+#include "gemm_tc2.cuh"
+
+namespace dwbc {
+
+constexpr int C2_MAX_OPS = 12, C2_MAX_LOADS = 6, C2_MAX_PACK = 26;
+constexpr int C2_TILE = 128 * 128;                       // floats per operand tile
+constexpr int C2_WORKERS = 16;                           // epilogue / load warps: lane quarter = warp % 4, column group = warp / 4
+constexpr int C2_THREADS = 32 * (C2_WORKERS + 1);        // + the MMA warp (warp 16)
+constexpr int C2_NW = 32 * C2_WORKERS;                   // 512 worker threads
+constexpr int C2_SMEM_FLOATS = 3 * C2_TILE + 2 * 128;    // tile X, tile Y, weight image, two bias slots
+
+enum { FIN_NONE = 0, FIN_ACT = 1, FIN_PPO = 2, FIN_VALUE = 3, FIN_REG = 4 };
+
+struct C2Load {
+  RowMat src;        // rows of the source (already offset to the first column)
+  int ncols;         // columns copied (multiple of 4)
+  int col0;          // destination column (multiple of 4)
+  int zero_to;       // columns [col0 + ncols, zero_to) are zero-filled (K padding of the consuming op)
+  int before_op;     // issued once the ops < before_op of the slot have retired (0: with the item)
+};
+struct C2Op {
+  const float* wp;       // packed image: canonical K-major [npad x kpad] weights, then [npad] bias
+  const float* wp_lo;    // 3xTF32: image of the low parts (no bias); null otherwise
+  float* y;              // global output (nullable), row-major
+  int64_t ldy;
+  int a_col0, kpad;      // first column of the A window inside the tile (multiple of 4), padded reduction length (multiple of 8)
+  int N, npad;           // outputs (npad: multiple of 16)
+  int act;               // forward: activation; backward: activation whose derivative multiplies
+  int out_col0;          // column of the tile the result is written to (multiple of 32), -1: none
+  int copy_after;        // 1: the global copy is taken from the tile after the slot has been handed back to the MMA thread
+  int mode;              // 0 forward (bias + act), 1 backward ((+ add) * act'(xact))
+  const float* xact; int64_t ldx;     // backward: activation OUTPUT [M x ldx] whose derivative multiplies; null: none
+  const float* add; int64_t ldadd;    // backward: optional addend [M x ldadd]
+  int fin, fin_c;        // epilogue hook of a head's last op and its channel (0 leg, 1 arm)
+};
+struct C2Prog {
+  int M, n_loads, n_ops;
+  C2Load ld[C2_MAX_LOADS];
+  C2Op op[C2_MAX_OPS];
+};
+
+// everything the epilogue hooks need (AC:326-345, PPO:166-221)
+struct FinArgs {
+  const float* std;                                          // [n_act]
+  // FIN_ACT (rollout): a = mu + std * eps
+  const float* eps; float* actions; float* log_prob; float* mean_out; float* sigma_out;
+  // FIN_PPO / FIN_VALUE / FIN_REG (update)
+  const int64_t* idx;                                        // mini-batch gather index (storage row of mini-batch row r)
+  const float* s_actions; const float* old_logp; const float* old_values; const float* returns; const float* adv;
+  const float* zh; int64_t zh_ld; int zh_by_src;
+  float* g_leg; int gleg_ld; float* g_arm; int garm_ld; float* g_v; int gv_ld; float* g_z; int gz_ld;
+  float* grad_std; float* losses;
+  int n_leg, n_act, latent, rows;
+  float clip, c_value, c_ent, c_reg, rho;
+  int clipped_value;
+};
+
+struct C2Launch {
+  int nprog, x3, pair;       // programs (1 or 2), error-compensated mode, tiles per work item (1 or 2)
+  int* queue;                // [2] device counters (next item, finished CTAs), zero between launches
+  C2Prog p[2];
+  FinArgs fin;
+};
+
+// ---- weight packing ---------------------------------------------------------------------------------------------------
+// image(n, k) of an op: up to two column segments of the source map into the K window of the tile,
+//   transpose = 0: image(n, k) = w[n * ldw + ksrc]     (forward: W [N x K])
+//   transpose = 1: image(n, k) = w[ksrc * ldw + n]     (backward: W [Kout x Nin], D = dZ W)
+// for k = kdst + j, ksrc = ksrc0 + j, j < len; zero elsewhere and for n >= N.  With `lo` the image of w - trunc_tf32(w) is written too.
+struct C2PackSeg { int kdst, ksrc, len; };
+struct C2PackItem { const float* w; int64_t ldw; const float* bias; int N, npad, kpad, transpose, nseg; C2PackSeg seg[2]; int64_t dst, dst_lo; };
+struct C2PackList { int n; float* out; C2PackItem it[C2_MAX_PACK]; };
+
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void pack_weights2_kernel(const __grid_constant__ C2PackList pl) {
+  const C2PackItem& it = pl.it[blockIdx.y];
+  const int wn = it.npad * it.kpad, total = wn + it.npad;
+  float* dst = pl.out + it.dst;
+  float* dlo = it.dst_lo >= 0 ? pl.out + it.dst_lo : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < wn) {
+      const int n = i / it.kpad, k = i - n * it.kpad;
+      float v = 0.0f;
+      if (n < it.N) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (s < it.nseg) {
+            const int j = k - it.seg[s].kdst;
+            if (j >= 0 && j < it.seg[s].len) {
+              const int ks = it.seg[s].ksrc + j;
+              v = it.transpose ? it.w[(int64_t)ks * it.ldw + n] : it.w[(int64_t)n * it.ldw + ks];
+            }
+          }
+        }
+      }
+      const size_t o = ((size_t)((n >> 3) * (it.kpad >> 2) + (k >> 2)) * 8 + (n & 7)) * 4 + (k & 3);
+      dst[o] = v;
+      if (dlo) dlo[o] = tf32_lo(v);
+    } else {
+      const int n = i - wn;
+      dst[i] = (it.bias && n < it.N) ? it.bias[n] : 0.0f;
+    }
+  }
+}
+
+// ---- device helpers ---------------------------------------------------------------------------------------------------
+struct C2Shared {
+  uint64_t w_full, w_free, ready[2], mma_done[2];
+  uint32_t tmem_base;
+  int item;
+};
+
+__device__ __forceinline__ void c2_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void c2_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc_smem_u32(dst_smem)), "l"(src),
+               "r"(bytes), "r"(tc_smem_u32(bar))
+               : "memory");
+}
+// tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void c2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns: registers -> tensor memory (thread = lane = row)
+__device__ __forceinline__ void c2_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void c2_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void c2_wbar() { asm volatile("bar.sync 1, %0;" ::"n"(C2_NW) : "memory"); }     // the sixteen worker warps
+
+constexpr float C2_LOG_SQRT_2PI = 0.91893853320467274178f;
+
+template <int kAct>
+__device__ __forceinline__ void c2_bias_act(float* v, const float* bias, int nvalid) {
+  if (kAct == ACT_TANH) {                 // narrow output heads only: skip the columns beyond N
+    for (int jj = 0; jj < 32; ++jj) v[jj] = jj < nvalid ? t2_tanh(v[jj] + bias[jj]) : 0.0f;
+    return;
+  }
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) {
+    float x = v[jj] + bias[jj];
+    if (kAct == ACT_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;
+    v[jj] = jj < nvalid ? x : 0.0f;
+  }
+}
+
+// ---- epilogue hooks: one thread per row, v[0 .. N) = the head's outputs of that row ---------------------------------------
+// FIN_ACT (PPO:119-123, AC:326-345): group c = 0 legs (columns [0, n_leg)), 1 arm ([n_leg, n_act))
+__device__ __forceinline__ void c2_fin_act(const FinArgs& f, int c, int64_t m, bool on, const float* v) {
+  if (!on) return;
+  const int off = c == 0 ? 0 : f.n_leg, cnt = c == 0 ? f.n_leg : f.n_act - f.n_leg;
+  float lp = 0.0f;
+  for (int i = 0; i < cnt; ++i) {
+    const float mu = v[i], sg = f.std[off + i];
+    const float a = mu + sg * f.eps[m * f.n_act + off + i];
+    const float d = a - mu;
+    lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
+    f.actions[m * f.n_act + off + i] = a;
+    f.mean_out[m * f.n_act + off + i] = mu;
+    f.sigma_out[m * f.n_act + off + i] = sg;
+  }
+  f.log_prob[2 * m + c] = lp;
+}
+// FIN_PPO (AC:341-345, PPO:199-205): log-prob of the stored action, ratio, mixed advantage, clipped surrogate, entropy and
+// the gradients w.r.t. the mean (through the tanh, AC:157,170) and std of this group
+__device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, bool on, const float* v, int lane) {
+  const int off = c == 0 ? 0 : f.n_leg, cnt = c == 0 ? f.n_leg : f.n_act - f.n_leg;
+  const float inv2m = 1.0f / (2.0f * (float)f.rows);
+  float l_surr = 0.0f, l_ent = 0.0f, glp = 0.0f;
+  int64_t src = 0;
+  if (on) {
+    src = f.idx ? f.idx[m] : m;
+    const float* act = f.s_actions + src * f.n_act + off;
+    float lp = 0.0f;
+    for (int i = 0; i < cnt; ++i) {
+      const float sg = f.std[off + i], d = act[i] - v[i];
+      lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
+      l_ent += 0.5f + C2_LOG_SQRT_2PI + logf(sg);
+    }
+    const float a0 = f.adv[2 * src], a1 = f.adv[2 * src + 1];
+    const float mix = c == 0 ? a0 + f.rho * a1 : a1 + f.rho * a0;                   // PPO:199-201
+    const float ratio = expf(lp - f.old_logp[2 * src + c]);                          // PPO:202
+    const float rc = fminf(fmaxf(ratio, 1.0f - f.clip), 1.0f + f.clip);
+    const float s1 = -mix * ratio, s2 = -mix * rc;                                   // PPO:203-205
+    l_surr = fmaxf(s1, s2);
+    const bool inside = ratio >= 1.0f - f.clip && ratio <= 1.0f + f.clip;
+    float g;
+    if (s1 > s2) g = -mix;
+    else if (s1 == s2) g = 0.5f * -mix + (inside ? 0.5f * -mix : 0.0f);
+    else g = inside ? -mix : 0.0f;
+    glp = inv2m * g * ratio;
+    float* grow = c == 0 ? f.g_leg + m * f.gleg_ld : f.g_arm + m * f.garm_ld;
+    const int gld = c == 0 ? f.gleg_ld : f.garm_ld;
+    for (int i = 0; i < gld; ++i) {
+      float gm = 0.0f;
+      if (i < cnt) {
+        const float sg = f.std[off + i], d = act[i] - v[i];
+        gm = glp * d / (sg * sg) * (1.0f - v[i] * v[i]);
+      }
+      grow[i] = gm;
+    }
+  }
+  for (int i = 0; i < cnt; ++i) {              // gradient of std: one atomic per warp and column
+    float gs = 0.0f;
+    if (on) {
+      const float sg = f.std[off + i], d = f.s_actions[src * f.n_act + off + i] - v[i];
+      gs = glp * ((d * d) / (sg * sg * sg) - 1.0f / sg) - f.c_ent * inv2m / sg;
+    }
+    gs = warp_sum(gs);
+    if (lane == 0) atomicAdd(f.grad_std + off + i, gs);
+  }
+  const float ss = warp_sum(l_surr * inv2m), se = warp_sum(l_ent * inv2m);
+  if (lane == 0) { atomicAdd(f.losses + 0, ss); atomicAdd(f.losses + 3, se); }
+}
+// FIN_VALUE (PPO:209-216), channel c
+__device__ __forceinline__ void c2_fin_value(const FinArgs& f, int c, int64_t m, bool on, float val, int lane) {
+  const float inv2m = 1.0f / (2.0f * (float)f.rows);
+  float l_val = 0.0f;
+  if (on) {
+    const int64_t src = f.idx ? f.idx[m] : m;
+    const float vo = f.old_values[2 * src + c], R = f.returns[2 * src + c];
+    const float l1 = (val - R) * (val - R);
+    float gv;
+    if (f.clipped_value) {
+      const float dvo = val - vo;
+      const float vc = vo + fminf(fmaxf(dvo, -f.clip), f.clip);
+      const float l2 = (vc - R) * (vc - R);
+      const bool inside = dvo >= -f.clip && dvo <= f.clip;
+      l_val = fmaxf(l1, l2);
+      const float g1 = 2.0f * (val - R), g2 = inside ? 2.0f * (vc - R) : 0.0f;
+      gv = l1 > l2 ? g1 : (l1 == l2 ? 0.5f * g1 + 0.5f * g2 : g2);
+    } else {
+      l_val = l1;
+      gv = 2.0f * (val - R);
+    }
+    f.g_v[m * f.gv_ld + c] = gv * f.c_value * inv2m;
+    if (c == 0) for (int i = 2; i < f.gv_ld; ++i) f.g_v[m * f.gv_ld + i] = 0.0f;     // pad columns are operand columns of the backward pass
+  }
+  const float s = warp_sum(l_val * inv2m);
+  if (lane == 0) atomicAdd(f.losses + 1, s);
+}
+// FIN_REG (PPO:174-177): || z_priv - sg(z_hist) ||_2 per row, mean over rows
+__device__ __forceinline__ void c2_fin_reg(const FinArgs& f, int64_t m, bool on, const float* v, int lane) {
+  const float invm = 1.0f / (float)f.rows;
+  float nrm = 0.0f;
+  if (on) {
+    const int64_t src = f.idx ? f.idx[m] : m;
+    const float* zhr = f.zh + (f.zh_by_src ? src : m) * f.zh_ld;
+    for (int i = 0; i < f.latent; ++i) { const float d = v[i] - zhr[i]; nrm += d * d; }
+    nrm = sqrtf(nrm);
+    const float s = nrm > 0.0f ? f.c_reg * invm / nrm : 0.0f;
+    for (int i = 0; i < f.gz_ld; ++i) f.g_z[m * f.gz_ld + i] = i < f.latent ? s * (v[i] - zhr[i]) : 0.0f;
+  }
+  const float s = warp_sum(nrm * invm);
+  if (lane == 0) atomicAdd(f.losses + 2, s);
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_constant__ C2Launch L, const int tiles) {
+  extern __shared__ __align__(1024) float c2_smem[];
+  __shared__ C2Shared sh;
+  float* tile[2] = {c2_smem, c2_smem + C2_TILE};
+  float* wbuf = c2_smem + 2 * C2_TILE;
+  float* bias_s = c2_smem + 3 * C2_TILE;                 // two slots of 128 (parity of the CTA-wide op counter)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    tc_mbar_init(&sh.w_full, 1);
+    tc_mbar_init(&sh.w_free, 1);
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&sh.ready[s], C2_NW); tc_mbar_init(&sh.mma_done[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == C2_WORKERS) tc_tmem_alloc(&sh.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+  const int pairs = (tiles + L.pair - 1) / L.pair;       // work items per program
+  const int items = pairs * L.nprog;
+  const bool x3 = L.x3 != 0;
+
+  // running counters, identical in every thread: ops of all items so far (bias slot parity) and ops per slot (phase of that
+  // slot's ready / mma_done barriers: a slot without a tile in some item does not advance)
+  uint32_t nop = 0, cnt[2] = {0, 0};
+  uint32_t nw = 0, nf = 0;          // weight images fetched (phase of w_full) / released (phase of w_free): used by the MMA thread only
+
+  for (;;) {
+    // ---- next work item ----
+    __syncthreads();                                     // everybody is done with the previous item (sh.item may be overwritten)
+    if (tid == 0) sh.item = atomicAdd(L.queue, 1);
+    __syncthreads();
+    const int item = sh.item;
+    if (item >= items) break;
+    const int pi = item / pairs;                         // program 0 (the longer one) first
+    const C2Prog& pr = L.p[pi];
+    const int t0 = (item - pi * pairs) * L.pair;
+    const int nslots = min(L.pair, tiles - t0);
+    const int nops = pr.n_ops;
+
+    if (warp == C2_WORKERS) {
+      // ===================== weight copies + MMA issue (one thread) =====================
+      if (lane == 0) {
+        const uint32_t b0 = tc_smem_u32(wbuf);
+        auto fetch = [&](const float* img, uint32_t wbytes, uint32_t bbytes, uint32_t slot) {
+          c2_expect_tx(&sh.w_full, wbytes + bbytes);
+          c2_bulk_g2s(wbuf, img, wbytes, &sh.w_full);
+          if (bbytes) c2_bulk_g2s(bias_s + slot * 128, img + (wbytes >> 2), bbytes, &sh.w_full);
+        };
+        uint32_t n = nop;
+        {
+          const C2Op& o0 = pr.op[0];
+          fetch(o0.wp, (uint32_t)(o0.npad * o0.kpad) * 4u, (uint32_t)o0.npad * 4u, n & 1);
+        }
+        for (int i = 0; i < nops; ++i, ++n) {
+          const C2Op& o = pr.op[i];
+          const uint32_t idesc = tc_idesc(o.npad, false, false);
+          const uint32_t wsbo = (uint32_t)(o.kpad >> 2) * 128u;
+          tc_mbar_wait(&sh.w_full, nw & 1); ++nw;
+          for (int s = 0; s < nslots; ++s) {
+            tc_mbar_wait(&sh.ready[s], (cnt[s] + i) & 1);   // loads landed / previous epilogue done: operand tile written, accumulator drained
+            tc_fence_async_smem();                       // generic-proxy tile writes -> async-proxy MMA reads
+            tc_fence_after();
+            const uint32_t a0 = tc_smem_u32(tile[s]) + (uint32_t)(o.a_col0 >> 2) * 128u;
+            const uint32_t dt = tmem + s * 256;
+            for (int kk = 0; kk < o.kpad; kk += 8)
+              tc_mma_tf32(dt, tc_desc(a0 + (kk >> 2) * 128, 128, 4096), tc_desc(b0 + (kk >> 2) * 128, 128, wsbo), idesc, kk > 0 ? 1u : 0u);
+            if (x3) {
+              for (int kk = 0; kk < o.kpad; kk += 8)
+                c2_mma_ts(dt, dt + 128 + o.a_col0 + kk, tc_desc(b0 + (kk >> 2) * 128, 128, wsbo), idesc, 1u);
+            } else {
+              tc_commit(&sh.mma_done[s]);
+            }
+          }
+          tc_commit(&sh.w_free);
+          tc_mbar_wait(&sh.w_free, nf & 1); ++nf;        // every MMA reading the image has retired: the buffer may be refilled
+          if (x3) {
+            fetch(o.wp_lo, (uint32_t)(o.npad * o.kpad) * 4u, 0u, 0);
+            tc_mbar_wait(&sh.w_full, nw & 1); ++nw;
+            for (int s = 0; s < nslots; ++s) {
+              const uint32_t a0 = tc_smem_u32(tile[s]) + (uint32_t)(o.a_col0 >> 2) * 128u;
+              const uint32_t dt = tmem + s * 256;
+              for (int kk = 0; kk < o.kpad; kk += 8)
+                tc_mma_tf32(dt, tc_desc(a0 + (kk >> 2) * 128, 128, 4096), tc_desc(b0 + (kk >> 2) * 128, 128, wsbo), idesc, 1u);
+              tc_commit(&sh.mma_done[s]);
+            }
+            tc_commit(&sh.w_free);
+            tc_mbar_wait(&sh.w_free, nf & 1); ++nf;
+          }
+          if (i + 1 < nops) {
+            const C2Op& o1 = pr.op[i + 1];
+            fetch(o1.wp, (uint32_t)(o1.npad * o1.kpad) * 4u, (uint32_t)o1.npad * 4u, (n + 1) & 1);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      // ===================== loads + epilogues (sixteen warps) =====================
+      const int q = warp & 3, h = warp >> 2;               // TMEM lane quarter, column group (32-column chunks ci with ci % 4 == h)
+      const int r = q * 32 + lane;                         // tile row of this thread in the epilogue
+      const int lrow = warp * 8 + (lane & 7), lpc = lane >> 3;   // load role: fixed row, 16-byte pieces lpc, lpc + 4, ...
+
+      // cp.async of one load into the tile of slot s (no waiting); rows beyond the matrix are zero-filled
+      auto issue_load = [&](const C2Load& ld, int s, int64_t m0, int rows) {
+        float* tl = tile[s];
+        const int c40 = ld.col0 >> 2, cpr = ld.ncols >> 2;
+        const int z0 = (ld.col0 + ld.ncols) >> 2, z1 = ld.zero_to >> 2;
+        float* rowbase = tl + ((size_t)(lrow >> 3) * 32) * 32 + (lrow & 7) * 4;
+        for (int cz = z0 + lpc; cz < z1; cz += 4) *reinterpret_cast<float4*>(rowbase + (size_t)cz * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool on = lrow < rows;
+        const float* src = on ? ld.src.row(m0 + lrow) : ld.src.p;
+        const uint32_t d0 = tc_smem_u32(rowbase);
+        for (int cc = lpc; cc < cpr; cc += 4)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + (uint32_t)(c40 + cc) * 128u), "l"(src + 4 * cc), "r"(on ? 16 : 0)
+                       : "memory");
+      };
+      // 3xTF32: low parts of tile columns [c_lo, c_hi) (whole 32-column chunks) -> A_lo of slot s
+      auto split_cols = [&](int s, int c_lo, int c_hi) {
+        const float* trow = tile[s] + ((size_t)(r >> 3) * 32) * 32 + (r & 7) * 4;
+        for (int ci = (c_lo >> 5) + h; ci * 32 < c_hi; ci += 4) {
+          float v[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = *reinterpret_cast<const float4*>(trow + (size_t)(ci * 8 + j4) * 32);
+            v[4 * j4] = tf32_lo(t.x); v[4 * j4 + 1] = tf32_lo(t.y); v[4 * j4 + 2] = tf32_lo(t.z); v[4 * j4 + 3] = tf32_lo(t.w);
+          }
+          c2_st32(tmem + s * 256 + 128 + ((uint32_t)(q * 32) << 16) + ci * 32, v);
+        }
+        c2_wait_st();
+      };
+      // loads of the slot that precede op `before`: issue, wait, (split), hand over
+      auto do_loads = [&](int before, bool sync_first) {
+        bool any = false;
+        for (int l = 0; l < pr.n_loads; ++l) any |= pr.ld[l].before_op == before;
+        if (!any) return false;
+        if (sync_first) c2_wbar();                       // every worker has finished writing / copying the tiles the loads overwrite
+        for (int s = 0; s < nslots; ++s) {
+          const int64_t m0 = (int64_t)(t0 + s) * TC_M;
+          const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
+          for (int l = 0; l < pr.n_loads; ++l)
+            if (pr.ld[l].before_op == before) issue_load(pr.ld[l], s, m0, rows);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (x3) {
+          c2_wbar();                                     // the pieces were copied by other threads than the ones that split them
+          for (int s = 0; s < nslots; ++s)
+            for (int l = 0; l < pr.n_loads; ++l)
+              if (pr.ld[l].before_op == before) split_cols(s, pr.ld[l].col0, pr.ld[l].zero_to);
+        }
+        return true;
+      };
+
+      uint32_t n = nop;
+      // ---- item start: both slots' initial loads ----
+      do_loads(0, false);
+      tc_fence_before();
+      tc_fence_async_smem();
+      for (int s = 0; s < nslots; ++s) t2_arrive(&sh.ready[s]);
+
+      for (int i = 0; i < nops; ++i, ++n) {
+        const C2Op& o = pr.op[i];
+        const int c0 = 32 * h;                             // this warp's chunk (every op has at most four chunks)
+        const bool mine = c0 < o.npad;
+        for (int s = 0; s < nslots; ++s) {
+          const int64_t m0 = (int64_t)(t0 + s) * TC_M;
+          const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
+          const bool on = r < rows;
+          // backward: the activation chunk whose derivative multiplies, fetched while the MMAs run
+          float x[32];
+          const bool use_x = o.mode == 1 && o.xact != nullptr && mine;
+          if (use_x) {
+            const float* xr = o.xact + (m0 + r) * o.ldx + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (on && c0 + 4 * j4 < o.N) t = *reinterpret_cast<const float4*>(xr + 4 * j4);
+              x[4 * j4] = t.x; x[4 * j4 + 1] = t.y; x[4 * j4 + 2] = t.z; x[4 * j4 + 3] = t.w;
+            }
+          }
+          tc_mbar_wait(&sh.mma_done[s], (cnt[s] + i) & 1);
+          tc_fence_after();
+          float v[32];
+          if (mine) {
+            tc_ld32(tmem + s * 256 + ((uint32_t)(q * 32) << 16) + c0, v);
+            if (o.mode == 0) {
+              const float* bias = bias_s + (n & 1) * 128 + c0;
+              if (o.act == ACT_ELU) c2_bias_act<ACT_ELU>(v, bias, o.N - c0);
+              else if (o.act == ACT_TANH) c2_bias_act<ACT_TANH>(v, bias, o.N - c0);
+              else c2_bias_act<ACT_NONE>(v, bias, o.N - c0);
+            } else {
+              if (o.add != nullptr && on) {
+                const float* ar = o.add + (m0 + r) * o.ldadd + c0;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  if (c0 + 4 * j4 < o.N) {
+                    const float4 t = *reinterpret_cast<const float4*>(ar + 4 * j4);
+                    v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+                  }
+                }
+              }
+              if (use_x) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const float d = o.act == ACT_TANH ? 1.0f - x[jj] * x[jj] : (x[jj] > 0.0f ? 1.0f : x[jj] + 1.0f);   // AC ELU / tanh derivatives from the outputs
+                  v[jj] *= d;
+                }
+              }
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] = c0 + jj < o.N ? v[jj] : 0.0f;
+            }
+            if (o.out_col0 >= 0) {
+              float* otile = tile[s] + ((size_t)((r >> 3) * 32 + ((o.out_col0 + c0) >> 2)) * 8 + (r & 7)) * 4;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(otile + (size_t)j4 * 32) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+              if (x3) {
+                float lo[32];
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) lo[jj] = tf32_lo(v[jj]);
+                c2_st32(tmem + s * 256 + 128 + ((uint32_t)(q * 32) << 16) + o.out_col0 + c0, lo);
+                c2_wait_st();
+              }
+            }
+            if (o.fin != FIN_NONE && h == 0) {
+              if (o.fin == FIN_ACT) c2_fin_act(L.fin, o.fin_c, m0 + r, on, v);
+              else if (o.fin == FIN_PPO) c2_fin_ppo(L.fin, o.fin_c, m0 + r, on, v, lane);
+              else if (o.fin == FIN_VALUE) c2_fin_value(L.fin, o.fin_c, m0 + r, on, v[0], lane);
+              else c2_fin_reg(L.fin, m0 + r, on, v, lane);
+            }
+            if (o.y != nullptr && !o.copy_after && on) {       // straight from the registers: 128 contiguous bytes per thread
+              float* yr = o.y + (m0 + r) * o.ldy + c0;
+              if ((o.ldy & 3) == 0 && (o.N & 3) == 0) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                  if (c0 + 4 * j4 < o.N) *reinterpret_cast<float4*>(yr + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+              } else {
+                for (int jj = 0; jj < 32; ++jj)
+                  if (c0 + jj < o.N) yr[jj] = v[jj];
+              }
+            }
+          }
+          tc_fence_before();                               // tcgen05.ld / st of this op precede the hand-over
+          if (i + 1 < nops) {
+            bool pending = false;                          // loads that precede op i+1 cover both slots and follow the last slot's epilogue
+            for (int l = 0; l < pr.n_loads; ++l) pending |= pr.ld[l].before_op == i + 1;
+            if (!pending) {
+              tc_fence_async_smem();
+              t2_arrive(&sh.ready[s]);
+            } else if (s + 1 == nslots) {
+              do_loads(i + 1, true);
+              tc_fence_before();
+              tc_fence_async_smem();
+              for (int s2 = 0; s2 < nslots; ++s2) t2_arrive(&sh.ready[s2]);
+            }
+          }
+          if (mine && o.y != nullptr && o.copy_after) {
+            // global copy of the chunk this warp just wrote, out of the tile: 8 rows x 64 contiguous bytes per instruction
+            __syncwarp();
+            const int r8 = lane & 7, pp = lane >> 3;
+            const float* tl = tile[s];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int rr = q * 32 + g * 8 + r8;
+              if (rr >= rows) continue;
+              const float* trow = tl + ((size_t)((rr >> 3) * 32 + ((o.out_col0 + c0) >> 2)) * 8 + r8) * 4;
+              float* yr = o.y + (m0 + rr) * o.ldy + c0;
+#pragma unroll
+              for (int p0 = 0; p0 < 8; p0 += 4) {
+                const int piece = p0 + pp;
+                if (c0 + 4 * piece < o.N) *reinterpret_cast<float4*>(yr + 4 * piece) = *reinterpret_cast<const float4*>(trow + (size_t)piece * 32);
+              }
+            }
+          }
+        }
+      }
+    }
+    nop += nops;
+    for (int s = 0; s < nslots; ++s) cnt[s] += nops;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C2_WORKERS) tc_tmem_dealloc(tmem, 512);
+  if (tid == 0) {                        // the last CTA re-arms the queue for the next launch
+    __threadfence();
+    if (atomicAdd(L.queue + 1, 1) == (int)gridDim.x - 1) { L.queue[0] = 0; L.queue[1] = 0; __threadfence(); }
+  }
+}
+
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+inline bool c2_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+constexpr int64_t C2_PACK_FLOATS = (int64_t)4 * C2_MAX_PACK * (C2_TILE + 256);      // forward + backward lists, raw + low images
+
+inline int launch_pack2(const C2PackList& pl, cudaStream_t st) {
+  if (pl.n <= 0) return DWBC_OK;
+  pack_weights2_kernel<<<dim3(8, pl.n), 256, 0, st>>>(pl);
+  ++dwbc_launch_counter;
+  return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
+}
+
+// Keeps the pack list and the program in step.  `off` is the running float offset into the packed-weight buffer.
+struct C2Builder {
+  C2Prog pr{};
+  C2PackList* pl;
+  int64_t* off;
+  bool x3, ok = true;
+  C2Builder(C2PackList* pl_, int64_t* off_, int M, bool x3_) : pl(pl_), off(off_), x3(x3_) { pr.M = M; }
+  void load(RowMat src, int ncols, int col0, int zero_to, int before_op) {
+    if (pr.n_loads >= C2_MAX_LOADS || (ncols & 3) || (col0 & 3) || (zero_to & 3) || zero_to < col0 + ncols || zero_to > 128 || !c2_aligned(src.p) ||
+        (src.stride_g & 3) || (src.ld & 3) || src.rpg != 1) { ok = false; return; }
+    pr.ld[pr.n_loads++] = C2Load{src, ncols, col0, zero_to, before_op};
+  }
+  C2Op* push(const float* W, int64_t ldw, const float* bias, int N, int kpad, int transpose, int nseg, C2PackSeg s0, C2PackSeg s1) {
+    const int npad = (N + 15) & ~15;
+    if (pr.n_ops >= C2_MAX_OPS || pl->n >= C2_MAX_PACK || N <= 0 || N > 128 || kpad <= 0 || kpad > 128 || (kpad & 7)) { ok = false; return nullptr; }
+    C2PackItem& it = pl->it[pl->n++];
+    it = C2PackItem{W, ldw, bias, N, npad, kpad, transpose, nseg, {s0, s1}, *off, -1};
+    C2Op& o = pr.op[pr.n_ops++];
+    o = C2Op{};
+    o.wp = pl->out ? pl->out + *off : nullptr;
+    *off = (*off + (int64_t)npad * kpad + npad + 63) & ~(int64_t)63;       // 256-byte aligned images (bulk copies need 16)
+    if (x3) {
+      it.dst_lo = *off;
+      o.wp_lo = pl->out ? pl->out + *off : nullptr;
+      *off = (*off + (int64_t)npad * kpad + 63) & ~(int64_t)63;
+    }
+    o.kpad = kpad; o.N = N; o.npad = npad;
+    return &o;
+  }
+  // y = act(A[:, a_col0 : a_col0 + kpad] W'^T + b): W [N x ldw]; tile column a_col0 + seg.kdst + j multiplies W[:, seg.ksrc + j]
+  void fwd(const float* W, int64_t ldw, const float* bias, int N, int act, int a_col0, int kpad, int nseg, C2PackSeg s0, C2PackSeg s1, int out_col0,
+           float* y, int64_t ldy, int fin = FIN_NONE, int fin_c = 0) {
+    if ((a_col0 & 3) || a_col0 + kpad > 128 || (out_col0 >= 0 && ((out_col0 & 31) || out_col0 + ((N + 31) & ~31) > 128)) || (fin != FIN_NONE && N > 32)) { ok = false; return; }
+    C2Op* o = push(W, ldw, bias, N, kpad, 0, nseg, s0, s1);
+    if (!o) return;
+    o->y = y; o->ldy = ldy; o->a_col0 = a_col0; o->act = act; o->out_col0 = out_col0; o->mode = 0; o->fin = fin; o->fin_c = fin_c;
+  }
+  // dX[:, :Nin] = (dZ[:, a_col0 : a_col0 + kpad] W' (+ add)) (*) act'(xact): W [Kout x ldw] (row = output feature);
+  // tile column a_col0 + seg.kdst + j multiplies row seg.ksrc + j of W
+  void bwd(const float* W, int64_t ldw, int Nin, int a_col0, int kpad, C2PackSeg seg, int act, const float* xact, int64_t ldx, const float* add,
+           int64_t ldadd, int out_col0, float* y, int64_t ldy) {
+    if ((a_col0 & 3) || a_col0 + kpad > 128 || (Nin & 3) || (xact && ((ldx & 3) || !c2_aligned(xact))) || (add && ((ldadd & 3) || !c2_aligned(add))) ||
+        (out_col0 >= 0 && (out_col0 & 31))) { ok = false; return; }
+    C2Op* o = push(W, ldw, nullptr, Nin, kpad, 1, 1, seg, C2PackSeg{0, 0, 0});
+    if (!o) return;
+    o->y = y; o->ldy = ldy; o->a_col0 = a_col0; o->act = act; o->out_col0 = out_col0; o->mode = 1;
+    o->xact = act == ACT_NONE ? nullptr : xact; o->ldx = ldx; o->add = add; o->ldadd = ldadd;
+  }
+  // global copies may be taken from the tile after the hand-over only if nothing overwrites those tile columns before the
+  // same warp's next epilogue: same column mapping in the next op (out_col0 0 or none) and no load in between
+  void finish() {
+    for (int i = 0; i < pr.n_ops; ++i) {
+      C2Op& o = pr.op[i];
+      bool load_next = false;
+      for (int l = 0; l < pr.n_loads; ++l) load_next |= pr.ld[l].before_op == i + 1;
+      const bool next_ok = i + 1 == pr.n_ops || pr.op[i + 1].out_col0 <= 0;
+      o.copy_after = (o.y && o.out_col0 == 0 && !load_next && next_ok && (o.ldy & 3) == 0 && (o.N & 3) == 0 && c2_aligned(o.y)) ? 1 : 0;
+      if (o.y && (o.ldy & 3) == 0 && (o.N & 3) == 0 && !c2_aligned(o.y)) ok = false;   // vector stores need 16-byte aligned rows
+    }
+  }
+};
+
+// pr1 may be null.  The longer program goes first in the queue.
+inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fin, bool x3, int* queue, cudaStream_t st) {
+  C2Launch L{};
+  L.nprog = pr1 ? 2 : 1;
+  L.x3 = x3 ? 1 : 0;
+  L.queue = queue;
+  L.fin = fin;
+  if (pr1 && pr1->n_ops > pr0->n_ops) { L.p[0] = *pr1; L.p[1] = *pr0; }
+  else { L.p[0] = *pr0; if (pr1) L.p[1] = *pr1; }
+  for (int k = 0; k < L.nprog; ++k) {
+    const C2Prog& pr = L.p[k];
+    if (pr.M <= 0 || pr.M != L.p[0].M || pr.n_ops <= 0 || pr.n_ops > C2_MAX_OPS || pr.n_loads < 0 || pr.n_loads > C2_MAX_LOADS) return DWBC_ERR_ARG;
+  }
+  if (!queue) return DWBC_ERR_ARG;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = (L.p[0].M + TC_M - 1) / TC_M;
+  L.pair = tiles * L.nprog > sms ? 2 : 1;                  // small batches (rollout): one tile per item, spread over more SMs
+  const int items = ((tiles + L.pair - 1) / L.pair) * L.nprog;
+  const int grid = items < sms ? items : sms;
+  const size_t smem = (size_t)C2_SMEM_FLOATS * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DWBC_ERR_LAUNCH;
+    attr = true;
+  }
+  chain2_kernel<<<grid, C2_THREADS, smem, st>>>(L, tiles);
+  ++dwbc_launch_counter;
+  return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
+}
+
+}  // namespace dwbc
