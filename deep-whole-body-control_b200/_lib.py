@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdwbc.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_DOF, MAX_TERMS, MAX_IDX, MAX_SLOTS, NUM_METRICS, RAND_COLS, MAX_LAYERS = 24, 40, 8, 64, 10, 104, 4
 GS, DS = 28, 72
 GS_COL = dict(commands=0, goal_timer=3, traj_timesteps=4, traj_total_timesteps=5, ee_start_sphere=6, ee_goal_sphere=9,
@@ -92,7 +92,11 @@ class NetCfg(C.Structure):
         ("off_critic_w", i64 * MAX_LAYERS), ("off_critic_b", i64 * MAX_LAYERS),
         ("off_cleg_w", i64 * (MAX_LAYERS + 1)), ("off_cleg_b", i64 * (MAX_LAYERS + 1)),
         ("off_carm_w", i64 * (MAX_LAYERS + 1)), ("off_carm_b", i64 * (MAX_LAYERS + 1)),
+        ("precision", i32), ("reserved_", i32),
     ]
+
+
+PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 
 class PpoHyper(C.Structure):
@@ -126,7 +130,7 @@ _SIGS = {
     "dwbc_store_rewards": [vp, vp, vp, vp, vp, f32, vp, vp, i32, vp],
     "dwbc_gae": [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, i32, vp],
     "dwbc_normalize_advantages": [vp, vp, i64, vp],
-    "dwbc_policy_act": [vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp],
+    "dwbc_policy_act": [vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp],
     "dwbc_critic_values": [vp, vp, vp, i64, vp, i32, vp, vp],
     "dwbc_hist_latent": [vp, vp, vp, i64, vp, i64, i32, vp, vp],
     "dwbc_compute_torques": [vp, vp, vp, vp, vp, i32, vp],
@@ -134,7 +138,6 @@ _SIGS = {
     "dwbc_dagger_minibatch_grad": [vp, vp, vp, vp, i32, vp, vp, vp, vp],
     "dwbc_clip_adam_step": [vp, vp, vp, vp, i64, i64, vp, i32, vp, vp, vp],
     "dwbc_enforce_min_std": [vp, i64, vp, i32, vp],
-    "dwbc_set_mlp_precision": [i32],
 }
 EXPORTS = sorted(list(_SIGS) + ["dwbc_workspace_bytes", "dwbc_version", "dwbc_struct_sizes", "dwbc_launch_count"])
 
@@ -183,11 +186,17 @@ def check(rc: int, what: str):
         raise DwbcError(f"{what} failed: {_ERR.get(rc, rc)}")
 
 
-def ptr(t):
-    """Device pointer of a contiguous torch tensor (None -> NULL)."""
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA torch tensor (None -> NULL).  The kernels reinterpret raw memory, so a tensor of the
+    wrong dtype or on the host must fail here, loudly, instead of being misread (`dtype`: expected torch dtype or tuple)."""
     if t is None:
         return None
-    assert t.is_contiguous(), "dwbc kernels need contiguous buffers"
+    if not t.is_contiguous():
+        raise DwbcError("dwbc kernels need contiguous buffers")
+    if not t.is_cuda:
+        raise DwbcError("dwbc kernels need CUDA tensors (got a host tensor)")
+    if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+        raise DwbcError(f"dwbc kernel argument has dtype {t.dtype}, expected {dtype}")
     return t.data_ptr()
 
 

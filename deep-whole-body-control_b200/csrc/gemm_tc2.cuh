@@ -1,6 +1,5 @@
-// Warp-specialised, mbarrier-pipelined tcgen05 GEMM (TF32 in, FP32 accumulate in TMEM) -- the production
-// tensor-core path of the ActorCritic layers.  Same math / operand layouts as gemm_tc.cuh (which stays as the
-// simple single-stage reference implementation), but the three phases of a tile overlap:
+// Warp-specialised, mbarrier-pipelined tcgen05 GEMM (TF32 in, FP32 accumulate in TMEM) -- the layer-wise tensor-core
+// path (history encoder, DAgger update, network shapes the fused chains do not cover).  The three phases of a tile overlap:
 //
 //   warps 0-3  PRODUCERS : gather + pad the A operand of tile i+1 into shared-memory stage (i+1)%S while ...
 //   warp  4    MMA       : ... one thread issues the tcgen05.mma chain of tile i into TMEM accumulator i%2,
@@ -14,7 +13,7 @@
 // The gather index of a tile is prefetched to shared memory first so every operand load is a single round trip,
 // and each producer thread keeps 8 independent 16-byte loads in flight.
 #pragma once
-#include "gemm_tc.cuh"
+#include "tc_common.cuh"
 
 namespace dwbc {
 
@@ -482,13 +481,14 @@ inline int launch_gemm_tc2(const GemmArgs& g_in, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
 
-// precision mode of the ActorCritic GEMMs: 0 = fp32 CUDA cores (parity anchor), 1 = TF32 tcgen05 (defined in mlp.cu)
-extern int mlp_precision;
-extern int tc_simple;   // 1: single-stage reference kernel (gemm_tc.cuh) instead of the pipelined one
+// precision of the ActorCritic GEMMs of the current call (defined in mlp.cu): 0 = fp32 CUDA cores (parity anchor), 1 = TF32 tcgen05,
+// 2 = 3xTF32: the fused chain / grouped weight-gradient kernels compensate the truncation; these layer-wise GEMMs (history encoder,
+// DAgger) then run on the exact fp32 kernels
+extern thread_local int mlp_precision;
 
 template <int kMode>
 inline int dispatch_gemm(const GemmArgs& g, cudaStream_t st) {
-  if (mlp_precision == 1 && tc_shape_ok(kMode, g)) return tc_simple ? launch_gemm_tc<kMode>(g, st) : launch_gemm_tc2<kMode>(g, st);
+  if (mlp_precision == 1 && tc_shape_ok(kMode, g)) return launch_gemm_tc2<kMode>(g, st);
   return launch_gemm<kMode>(g, st);
 }
 

@@ -10,13 +10,14 @@
 
 #include <stdlib.h>
 
-#include "mlp_chain.cuh"
+#include "mlp_chain2.cuh"
 #include "wgrad_group.cuh"
 
 namespace dwbc {
 
-int mlp_precision = 0;
-int tc_simple = 0;
+// precision of the ActorCritic GEMMs of the CURRENT call (DwbcNetCfg.precision, set by every entry point):
+// 0 = fp32 CUDA cores (parity anchor), 1 = TF32 tcgen05, 2 = 3xTF32 tcgen05 (error-compensated, fp32-grade)
+thread_local int mlp_precision = 0;
 int tc_debug = 0;
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -51,7 +52,8 @@ struct Plan {
   float* hc2;                     // [rows*3, 12]
   float* zh;                      // [rows, latent]
   float* hw1; float* hw2; float* hwl;      // re-packed weights
-  float* wpack;                            // packed weight images of the fused chain kernels (mlp_chain.cuh)
+  float* wpack;                            // packed weight images of the fused chain kernels (mlp_chain2.cuh)
+  int* queue;                              // work-item counters of the chain kernel (zero between launches)
   // gradients
   float* g_leg; float* g_arm; float* g_vl; float* g_va; float* g_z;   // g_vl / g_va: columns 0 / 1 of one [rows, 4] buffer
   // per-layer pre-activation gradients kept by the fused backward chain for the weight-gradient GEMMs
@@ -95,7 +97,8 @@ static Plan make_plan(const DwbcNetCfg& n, int64_t rows, void* ws) {
   p.hc2 = b.f(rows * 3 * 12);
   p.zh = b.f(rows * align_up(p.latent, 4));
   p.hw1 = b.f(20 * 128); p.hw2 = b.f(10 * 40); p.hwl = b.f(32 * 36);
-  p.wpack = b.f((int64_t)2 * CH_MAX_PACK * (CH_WBUF + 64));
+  p.wpack = b.f(C2_PACK_FLOATS);
+  p.queue = reinterpret_cast<int*>(b.f(64));
   p.g_leg = b.f(rows * align_up(n.n_leg, 4)); p.g_arm = b.f(rows * align_up(n.n_arm, 4));
   p.g_vl = b.f(rows * 4); p.g_va = p.g_vl ? p.g_vl + 1 : nullptr; p.g_z = b.f(rows * align_up(p.latent, 4));
   for (int i = 0; i < n.n_leg_layers; ++i) { p.dza_l[i] = b.f(rows * n.leg_dims[i]); p.dzc_l[i] = b.f(rows * n.leg_dims[i]); }
@@ -114,7 +117,8 @@ static Plan make_plan(const DwbcNetCfg& n, int64_t rows, void* ws) {
 }
 
 static int check_net(const DwbcNetCfg* n) {
-  if (!n || n->abi_version != DWBC_ABI_VERSION) return DWBC_ERR_ARG;
+  if (!n || n->abi_version != DWBC_ABI_VERSION || n->precision < 0 || n->precision > 2) return DWBC_ERR_ARG;
+  mlp_precision = n->precision;
   if (n->n_priv_layers < 1 || n->n_priv_layers > DWBC_MAX_LAYERS || n->n_actor_layers < 1 || n->n_actor_layers > DWBC_MAX_LAYERS ||
       n->n_critic_layers < 1 || n->n_critic_layers > DWBC_MAX_LAYERS || n->n_leg_layers < 1 || n->n_leg_layers > DWBC_MAX_LAYERS ||
       n->n_arm_layers < 1 || n->n_arm_layers > DWBC_MAX_LAYERS)
@@ -276,78 +280,89 @@ static int critic_forward(const DwbcNetCfg& n, const float* P, const float* obs,
   return DWBC_OK;
 }
 
-// ---- fused forward (TF32 path): priv encoder + actor in ONE launch, critic in one launch (mlp_chain.cuh) --------------
+// ---- fused forward (tensor-core paths): privileged encoder + actor and the critic as two programs of ONE launch (mlp_chain2.cuh) ----
+static inline int pad8(int x) { return (x + 7) & ~7; }
+constexpr int C2_COL_PRIV = 32, C2_COL_HID = 64, C2_COL_PROP = 32;     // tile columns of the encoder input / hidden layer and of obs_prop (z sits at 0)
+
 static bool chain_usable(const DwbcNetCfg& n, const Plan& p, const float* obs, int64_t obs_stride) {
-  if (mlp_precision != 1 || tc_simple || getenv("DWBC_NO_CHAIN")) return false;
+  if (mlp_precision == 0) return false;
   auto ok = [](const int32_t* d, int k) { for (int i = 0; i < k; ++i) if (d[i] > 128 || (d[i] & 3)) return false; return true; };
   if (!ok(n.priv_dims, n.n_priv_layers) || !ok(n.actor_dims, n.n_actor_layers) || !ok(n.critic_dims, n.n_critic_layers) ||
       !ok(n.leg_dims, n.n_leg_layers) || !ok(n.arm_dims, n.n_arm_layers))
     return false;
-  if ((n.num_prop & 3) || (n.num_priv & 3) || (p.latent & 3) || n.num_prop + p.latent > 128 || n.num_prop + n.num_priv > 128 || n.num_priv > 128)
-    return false;
-  if ((obs_stride & 3) || !chain_aligned(obs)) return false;
-  if (n.n_priv_layers + n.n_actor_layers + n.n_leg_layers + n.n_arm_layers + 2 > CH_MAX_OPS) return false;
-  if (n.n_critic_layers + n.n_leg_layers + n.n_arm_layers + 2 > CH_MAX_OPS) return false;
+  // tile layout of the actor program: z at columns [0, 32), obs_prop at [32, 32 + num_prop), the encoder works at [32, 64) -> [64, 128) first
+  if (n.n_priv_layers != 2 || n.num_priv > 32 || n.priv_dims[0] > 64 || p.latent > 32) return false;
+  if ((n.num_prop & 3) || (n.num_priv & 3) || (p.latent & 3) || C2_COL_PROP + n.num_prop > 128 || n.num_prop + n.num_priv > 128) return false;
+  if ((obs_stride & 3) || !c2_aligned(obs)) return false;
+  if (2 + n.n_actor_layers + n.n_leg_layers + n.n_arm_layers + 2 > C2_MAX_OPS) return false;
+  if (n.n_critic_layers + n.n_leg_layers + n.n_arm_layers + 2 > C2_MAX_OPS) return false;
   return true;
 }
 
-static void chain_head(ChainBuilder& b, const float* P, int trunk_buf, int in, int nl, const int32_t* dims, int n_out, const int64_t* ow,
-                       const int64_t* ob, float* const* acts, bool store, float* out, int64_t ldo, int last_act) {
-  int a = trunk_buf;
-  for (int l = 0; l < nl; ++l) {          // hidden layers live in buffer 0 (the trunk stays intact in buffer 1 for the other head)
-    b.op(P + ow[l], in, P + ob[l], dims[l], in, ACT_ELU, a, 0, 0, store ? acts[l] : nullptr, dims[l]);
-    a = 0;
+// one head: optional trunk reload (the second head of a program), hidden layers in place, narrow last layer with its epilogue hook
+static void chain_head(C2Builder& b, const float* P, const float* trunk, int trunk_ld, bool reload, int in, int nl, const int32_t* dims, int n_out,
+                       const int64_t* ow, const int64_t* ob, float* const* acts, bool store, float* out, int64_t ldo, int last_act, int fin, int fin_c) {
+  if (reload) b.load(rowmat(trunk, trunk_ld), in, 0, pad8(in), b.pr.n_ops);
+  for (int l = 0; l < nl; ++l) {
+    b.fwd(P + ow[l], in, P + ob[l], dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0, store ? acts[l] : nullptr, dims[l]);
     in = dims[l];
   }
-  b.op(P + ow[nl], in, P + ob[nl], n_out, in, last_act, a, -1, 0, out, ldo);
+  b.fwd(P + ow[nl], in, P + ob[nl], n_out, last_act, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, -1, out, ldo, fin, fin_c);
 }
 
-// z_hist == nullptr: latent from the privileged encoder (computed inside the chain); else the history latent [rows, zld]
-static int forward_chains(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows,
-                          const float* z_hist, int zld, const Plan& p, float* value, bool store, bool actor, bool critic, cudaStream_t st) {
-  PackList pl{};
-  pl.out = p.wpack;
-  int64_t off = 0;
-  ChainBuilder A(&pl, &off, rows), C(&pl, &off, rows);
-  if (actor) {
+// Programs of the forward pass.  z_hist == nullptr: latent from the privileged encoder (computed inside the chain); else the history
+// latent [rows, zld].  `loss`: update mode (hooks FIN_REG / FIN_PPO / FIN_VALUE), else rollout mode (FIN_ACT), else none (fin_mode 0).
+static int build_forward(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, const float* z_hist, int zld,
+                         const Plan& p, float* value, bool store, int fin_mode, C2Builder* A, C2Builder* C) {
+  const int Lld = (int)align_up(p.latent, 4);
+  if (A) {
     const int in0 = n.num_prop + p.latent;
-    A.load(rowmat_gather(obs, idx, obs_stride), n.num_prop, 1, 0, z_hist ? n.num_prop : n.num_prop);
+    int first_main = 0;
     if (z_hist) {
-      A.load(rowmat(z_hist, zld), p.latent, 1, n.num_prop, (in0 + 7) & ~7);
+      A->load(rowmat(z_hist, zld), p.latent, 0, 32, 0);
     } else {
-      A.load(rowmat_gather(obs + n.num_prop, idx, obs_stride), n.num_priv, 0, 0, (n.num_priv + 7) & ~7);
-      int in = n.num_priv;
-      for (int l = 0; l < n.n_priv_layers; ++l) {                                  // AC:219-221
-        const bool lastl = l == n.n_priv_layers - 1;
-        A.op(P + n.off_priv_w[l], in, P + n.off_priv_b[l], n.priv_dims[l], in, ACT_ELU, 0, lastl ? 1 : 0, lastl ? n.num_prop : 0,
-             store ? p.priv[l] : nullptr, align_up(n.priv_dims[l], 4));
-        in = n.priv_dims[l];
-      }
+      A->load(rowmat_gather(obs + n.num_prop, idx, obs_stride), n.num_priv, C2_COL_PRIV, C2_COL_PRIV + pad8(n.num_priv), 0);
+      A->fwd(P + n.off_priv_w[0], n.num_priv, P + n.off_priv_b[0], n.priv_dims[0], ACT_ELU, C2_COL_PRIV, pad8(n.num_priv), 1,      // AC:219-221
+             C2PackSeg{0, 0, n.num_priv}, C2PackSeg{0, 0, 0}, C2_COL_HID, store ? p.priv[0] : nullptr, align_up(n.priv_dims[0], 4));
+      A->fwd(P + n.off_priv_w[1], n.priv_dims[0], P + n.off_priv_b[1], p.latent, ACT_ELU, C2_COL_HID, pad8(n.priv_dims[0]), 1,
+             C2PackSeg{0, 0, n.priv_dims[0]}, C2PackSeg{0, 0, 0}, 0, store ? p.priv[1] : nullptr, Lld, fin_mode == 2 ? FIN_REG : FIN_NONE, 0);
+      first_main = 2;
     }
-    int in = in0;
-    for (int l = 0; l < n.n_actor_layers; ++l) {                                   // AC:211-213, input cat([obs_prop, z]) sits in buffer 1
-      A.op(P + n.off_actor_w[l], in, P + n.off_actor_b[l], n.actor_dims[l], in, ACT_ELU, 1, 1, 0, store ? p.ab[l] : nullptr, n.actor_dims[l]);
+    const int k0 = pad8(C2_COL_PROP + n.num_prop);
+    A->load(rowmat_gather(obs, idx, obs_stride), n.num_prop, C2_COL_PROP, k0, first_main);
+    // backbone layer 0 over cat([obs_prop, z]) (AC:211): z occupies tile columns [0, latent), obs_prop [32, 32 + num_prop)
+    const int na = n.n_actor_layers;
+    A->fwd(P + n.off_actor_w[0], in0, P + n.off_actor_b[0], n.actor_dims[0], ACT_ELU, 0, k0, 2, C2PackSeg{0, n.num_prop, p.latent},
+           C2PackSeg{C2_COL_PROP, 0, n.num_prop}, 0, (store || na == 1) ? p.ab[0] : nullptr, n.actor_dims[0]);
+    int in = n.actor_dims[0];
+    for (int l = 1; l < na; ++l) {                                                   // AC:211-213
+      A->fwd(P + n.off_actor_w[l], in, P + n.off_actor_b[l], n.actor_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
+             (store || l == na - 1) ? p.ab[l] : nullptr, n.actor_dims[l]);
       in = n.actor_dims[l];
     }
-    chain_head(A, P, 1, in, n.n_leg_layers, n.leg_dims, n.n_leg, n.off_aleg_w, n.off_aleg_b, p.al, store, p.mean, p.mean_ld, ACT_TANH);
-    chain_head(A, P, 1, in, n.n_arm_layers, n.arm_dims, n.n_arm, n.off_aarm_w, n.off_aarm_b, p.aa, store, p.mean + n.n_leg, p.mean_ld, ACT_TANH);
-    if (!A.ok) return DWBC_ERR_UNSUPPORTED;
+    const int fin = fin_mode == 2 ? FIN_PPO : (fin_mode == 1 ? FIN_ACT : FIN_NONE);
+    float* mean = fin_mode == 0 ? p.mean : nullptr;
+    chain_head(*A, P, p.ab[na - 1], in, false, in, n.n_leg_layers, n.leg_dims, n.n_leg, n.off_aleg_w, n.off_aleg_b, p.al, store, mean, p.mean_ld, ACT_TANH, fin, 0);
+    chain_head(*A, P, p.ab[na - 1], in, true, in, n.n_arm_layers, n.arm_dims, n.n_arm, n.off_aarm_w, n.off_aarm_b, p.aa, store,
+               mean ? mean + n.n_leg : nullptr, p.mean_ld, ACT_TANH, fin, 1);
+    A->finish();
+    if (!A->ok) return DWBC_ERR_UNSUPPORTED;
   }
-  if (critic) {
+  if (C) {
     int in = n.num_prop + n.num_priv;
-    C.load(rowmat_gather(obs, idx, obs_stride), in, 1, 0, (in + 7) & ~7);
-    for (int l = 0; l < n.n_critic_layers; ++l) {                                  // AC:280-286
-      C.op(P + n.off_critic_w[l], in, P + n.off_critic_b[l], n.critic_dims[l], in, ACT_ELU, 1, 1, 0, store ? p.cb[l] : nullptr, n.critic_dims[l]);
+    C->load(rowmat_gather(obs, idx, obs_stride), in, 0, pad8(in), 0);
+    const int nc = n.n_critic_layers;
+    for (int l = 0; l < nc; ++l) {                                                   // AC:280-286
+      C->fwd(P + n.off_critic_w[l], in, P + n.off_critic_b[l], n.critic_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
+             (store || l == nc - 1) ? p.cb[l] : nullptr, n.critic_dims[l]);
       in = n.critic_dims[l];
     }
-    chain_head(C, P, 1, in, n.n_leg_layers, n.leg_dims, 1, n.off_cleg_w, n.off_cleg_b, p.cl, store, value, 2, ACT_NONE);
-    chain_head(C, P, 1, in, n.n_arm_layers, n.arm_dims, 1, n.off_carm_w, n.off_carm_b, p.ca, store, value + 1, 2, ACT_NONE);
-    if (!C.ok) return DWBC_ERR_UNSUPPORTED;
+    const int fin = fin_mode == 2 ? FIN_VALUE : FIN_NONE;
+    chain_head(*C, P, p.cb[nc - 1], in, false, in, n.n_leg_layers, n.leg_dims, 1, n.off_cleg_w, n.off_cleg_b, p.cl, store, value, 2, ACT_NONE, fin, 0);
+    chain_head(*C, P, p.cb[nc - 1], in, true, in, n.n_arm_layers, n.arm_dims, 1, n.off_carm_w, n.off_carm_b, p.ca, store, value + 1, 2, ACT_NONE, fin, 1);
+    C->finish();
+    if (!C->ok) return DWBC_ERR_UNSUPPORTED;
   }
-  TRY(launch_pack(pl, st));
-  if (actor && critic) TRY(launch_chain2(&A.pr, &C.pr, st));
-  else if (actor) TRY(launch_chain(A.pr, st));
-  else if (critic) TRY(launch_chain(C.pr, st));
   return DWBC_OK;
 }
 
@@ -545,25 +560,29 @@ static int head_backward(const float* P, float* grad, RowMat G_out, int n_out, i
   return DWBC_OK;
 }
 
-// ---- fused backward (TF32 path): all data-gradient GEMMs of the critic in one launch and of the actor + privileged
-// encoder in another (mlp_chain.cuh, backward ops); the per-layer pre-activation gradients they leave behind feed the
-// weight-gradient GEMMs (gemm_tc2.cuh, MN-major operands).
+// ---- fused backward (tensor-core paths): all data-gradient GEMMs of the actor + privileged encoder and of the critic as two
+// programs of one launch (mlp_chain2.cuh, backward ops); the per-layer pre-activation gradients they leave behind feed the
+// weight-gradient GEMMs (wgrad_group.cuh, MN-major operands).
 struct HeadDesc { int nl; const int32_t* dims; const int64_t* ow; const int64_t* ob; float* const* acts; float* const* dz; RowMat g_out; int n_out; };
 
-// data-gradient ops of one head, last layer first; the trunk gradient accumulates in TMEM slot 1 across the two heads
-static void chain_head_bwd(ChainBuilder& b, const float* P, const HeadDesc& hd, int a_col0, int k0, int kwin, int trunk_dim, const float* trunk,
-                           bool second, float* dz_trunk) {
+// data-gradient ops of one head, last layer first.  The head's loss gradient [rows, g_ld] is loaded into tile columns [0, g_ld) right
+// before its first op; column g_col + j of that window multiplies row j of the last layer's weights.  The trunk gradient of the
+// FIRST head goes to `scratch` unactivated; the second head adds it and applies the trunk's ELU'.
+static void chain_head_bwd(C2Builder& b, const float* P, const HeadDesc& hd, const float* g, int g_ld, int g_col, int trunk_dim, const float* trunk,
+                           bool second, float* scratch, float* dz_trunk) {
+  b.load(rowmat(g, g_ld), g_ld, 0, pad8(g_ld), b.pr.n_ops);
   for (int l = hd.nl; l >= 0; --l) {
     const int in = l == 0 ? trunk_dim : hd.dims[l - 1];
     const int out = l == hd.nl ? hd.n_out : hd.dims[l];
-    const bool from_narrow = l == hd.nl;
-    if (l > 0) {
-      b.bwd(P + hd.ow[l], in, in, out, from_narrow ? k0 : 0, from_narrow ? kwin : out, ACT_ELU, hd.acts[l - 1], in, nullptr, 0,
-            from_narrow ? 2 : 0, from_narrow ? a_col0 : 0, 0, hd.dz[l - 1], in, 0, 0, 0);
-    } else {
-      b.bwd(P + hd.ow[0], in, in, out, from_narrow ? k0 : 0, from_narrow ? kwin : out, ACT_ELU, trunk, trunk_dim, nullptr, 0,
-            from_narrow ? 2 : 0, from_narrow ? a_col0 : 0, 0, second ? dz_trunk : nullptr, trunk_dim, 1, second ? 1 : 0, second ? 0 : 1);
-    }
+    const bool narrow = l == hd.nl;
+    const int kpad = narrow ? pad8(g_ld) : pad8(out);
+    const C2PackSeg seg{narrow ? g_col : 0, 0, out};
+    if (l > 0)
+      b.bwd(P + hd.ow[l], in, in, 0, kpad, seg, ACT_ELU, hd.acts[l - 1], in, nullptr, 0, 0, hd.dz[l - 1], in);
+    else if (!second)
+      b.bwd(P + hd.ow[0], in, in, 0, kpad, seg, ACT_NONE, nullptr, 0, nullptr, 0, -1, scratch, trunk_dim);
+    else
+      b.bwd(P + hd.ow[0], in, in, 0, kpad, seg, ACT_ELU, trunk, trunk_dim, scratch, trunk_dim, 0, dz_trunk, trunk_dim);
   }
 }
 
@@ -577,60 +596,70 @@ static void head_wgrad(WGroupBuilder& wb, float* grad, const HeadDesc& hd, RowMa
   }
 }
 
-static int backward_chains(const DwbcNetCfg& n, const float* P, float* grad, const DwbcStorage* s, const int64_t* idx, int rows, const Plan& p,
-                           cudaStream_t st) {
+struct BwdDescs { HeadDesc cl, ca, al, aa; };
+static BwdDescs bwd_descs(const DwbcNetCfg& n, const Plan& p) {
+  const int gleg_ld = (int)align_up(n.n_leg, 4), garm_ld = (int)align_up(n.n_arm, 4);
+  BwdDescs d;
+  d.cl = HeadDesc{n.n_leg_layers, n.leg_dims, n.off_cleg_w, n.off_cleg_b, p.cl, p.dzc_l, rowmat(p.g_vl, 4), 1};
+  d.ca = HeadDesc{n.n_arm_layers, n.arm_dims, n.off_carm_w, n.off_carm_b, p.ca, p.dzc_a, rowmat(p.g_va, 4), 1};
+  d.al = HeadDesc{n.n_leg_layers, n.leg_dims, n.off_aleg_w, n.off_aleg_b, p.al, p.dza_l, rowmat(p.g_leg, gleg_ld), n.n_leg};
+  d.aa = HeadDesc{n.n_arm_layers, n.arm_dims, n.off_aarm_w, n.off_aarm_b, p.aa, p.dza_a, rowmat(p.g_arm, garm_ld), n.n_arm};
+  return d;
+}
+
+static int build_backward(const DwbcNetCfg& n, const float* P, const Plan& p, C2Builder& A, C2Builder& C) {
   const int Lld = (int)align_up(p.latent, 4);
   const int gleg_ld = (int)align_up(n.n_leg, 4), garm_ld = (int)align_up(n.n_arm, 4);
-  PackList pl{};
-  pl.out = p.wpack + (int64_t)CH_MAX_PACK * (CH_WBUF + 64);      // second half of the pack buffer (the forward images stay valid)
-  int64_t off = 0;
-  ChainBuilder C(&pl, &off, rows), A(&pl, &off, rows);
-  // ---- critic ----
+  const BwdDescs d = bwd_descs(n, p);
+  // ---- critic: both value heads read their column of the [rows, 4] value-gradient buffer ----
   const int cnb = n.n_critic_layers, ctd = n.critic_dims[cnb - 1];
-  HeadDesc cl{n.n_leg_layers, n.leg_dims, n.off_cleg_w, n.off_cleg_b, p.cl, p.dzc_l, rowmat(p.g_vl, 4), 1};
-  HeadDesc ca{n.n_arm_layers, n.arm_dims, n.off_carm_w, n.off_carm_b, p.ca, p.dzc_a, rowmat(p.g_va, 4), 1};
-  C.load(rowmat(p.g_vl, 4), 4, 2, 0, 8);
-  chain_head_bwd(C, P, cl, 0, 0, 8, ctd, p.cb[cnb - 1], false, nullptr);
-  chain_head_bwd(C, P, ca, 0, 1, 8, ctd, p.cb[cnb - 1], true, p.dzc_b[cnb - 1]);
+  chain_head_bwd(C, P, d.cl, p.g_vl, 4, 0, ctd, p.cb[cnb - 1], false, p.d1, nullptr);
+  chain_head_bwd(C, P, d.ca, p.g_vl, 4, 1, ctd, p.cb[cnb - 1], true, p.d1, p.dzc_b[cnb - 1]);
   for (int l = cnb - 1; l >= 1; --l)
-    C.bwd(P + n.off_critic_w[l], n.critic_dims[l - 1], n.critic_dims[l - 1], n.critic_dims[l], 0, n.critic_dims[l], ACT_ELU, p.cb[l - 1],
-          n.critic_dims[l - 1], nullptr, 0, 0, 0, 0, p.dzc_b[l - 1], n.critic_dims[l - 1], 0, 0, 0);
+    C.bwd(P + n.off_critic_w[l], n.critic_dims[l - 1], n.critic_dims[l - 1], 0, pad8(n.critic_dims[l]), C2PackSeg{0, 0, n.critic_dims[l]}, ACT_ELU,
+          p.cb[l - 1], n.critic_dims[l - 1], nullptr, 0, l - 1 > 0 ? 0 : -1, p.dzc_b[l - 1], n.critic_dims[l - 1]);
+  C.finish();
   // ---- actor + privileged encoder ----
   const int anb = n.n_actor_layers, atd = n.actor_dims[anb - 1];
-  HeadDesc al{n.n_leg_layers, n.leg_dims, n.off_aleg_w, n.off_aleg_b, p.al, p.dza_l, rowmat(p.g_leg, gleg_ld), n.n_leg};
-  HeadDesc aa{n.n_arm_layers, n.arm_dims, n.off_aarm_w, n.off_aarm_b, p.aa, p.dza_a, rowmat(p.g_arm, garm_ld), n.n_arm};
-  const int kw_leg = (gleg_ld + 7) & ~7, kw_arm = (garm_ld + 7) & ~7;
-  A.load(rowmat(p.g_leg, gleg_ld), gleg_ld, 2, 0, kw_leg);
-  A.load(rowmat(p.g_arm, garm_ld), garm_ld, 2, kw_leg, kw_leg + kw_arm);
-  chain_head_bwd(A, P, al, 0, 0, kw_leg, atd, p.ab[anb - 1], false, nullptr);
-  chain_head_bwd(A, P, aa, kw_leg, 0, kw_arm, atd, p.ab[anb - 1], true, p.dza_b[anb - 1]);
+  chain_head_bwd(A, P, d.al, p.g_leg, gleg_ld, 0, atd, p.ab[anb - 1], false, p.d0, nullptr);
+  chain_head_bwd(A, P, d.aa, p.g_arm, garm_ld, 0, atd, p.ab[anb - 1], true, p.d0, p.dza_b[anb - 1]);
   for (int l = anb - 1; l >= 1; --l)
-    A.bwd(P + n.off_actor_w[l], n.actor_dims[l - 1], n.actor_dims[l - 1], n.actor_dims[l], 0, n.actor_dims[l], ACT_ELU, p.ab[l - 1],
-          n.actor_dims[l - 1], nullptr, 0, 0, 0, 0, p.dza_b[l - 1], n.actor_dims[l - 1], 0, 0, 0);
+    A.bwd(P + n.off_actor_w[l], n.actor_dims[l - 1], n.actor_dims[l - 1], 0, pad8(n.actor_dims[l]), C2PackSeg{0, 0, n.actor_dims[l]}, ACT_ELU,
+          p.ab[l - 1], n.actor_dims[l - 1], nullptr, 0, 0, p.dza_b[l - 1], n.actor_dims[l - 1]);
   const int in0 = n.num_prop + p.latent, np = n.n_priv_layers;
   float* z = p.priv[np - 1];
   // dL/dz = policy path through the latent columns of backbone layer 0 + privileged-latent regulariser (g_z), through the encoder's last ELU
-  A.bwd(P + n.off_actor_w[0] + n.num_prop, in0, p.latent, n.actor_dims[0], 0, n.actor_dims[0], ACT_ELU, z, Lld, p.g_z, Lld, 0, 0, 0, p.dzp[np - 1],
-        Lld, 0, 0, 0);
+  A.bwd(P + n.off_actor_w[0] + n.num_prop, in0, p.latent, 0, pad8(n.actor_dims[0]), C2PackSeg{0, 0, n.actor_dims[0]}, ACT_ELU, z, Lld, p.g_z, Lld, 0,
+        p.dzp[np - 1], Lld);
   for (int l = np - 1; l >= 1; --l) {
     const int in = n.priv_dims[l - 1], ldin = (int)align_up(in, 4);
-    A.bwd(P + n.off_priv_w[l], in, in, n.priv_dims[l], 0, n.priv_dims[l], ACT_ELU, p.priv[l - 1], ldin, nullptr, 0, 0, 0, 0, p.dzp[l - 1], ldin, 0, 0, 0);
+    A.bwd(P + n.off_priv_w[l], in, in, 0, pad8(n.priv_dims[l]), C2PackSeg{0, 0, n.priv_dims[l]}, ACT_ELU, p.priv[l - 1], ldin, nullptr, 0, l - 1 > 0 ? 0 : -1,
+          p.dzp[l - 1], ldin);
   }
-  if (!C.ok || !A.ok || kw_leg + kw_arm > 32) return DWBC_ERR_UNSUPPORTED;
-  TRY(launch_pack(pl, st));
-  TRY(launch_chain2(&A.pr, &C.pr, st));
-  // ---- weight gradients: every layer of both networks in one persistent launch (wgrad_group.cuh) ----
+  A.finish();
+  if (!C.ok || !A.ok) return DWBC_ERR_UNSUPPORTED;
+  return DWBC_OK;
+}
+
+// every layer's weight gradient of both networks in one persistent launch (wgrad_group.cuh)
+static int weight_gradients(const DwbcNetCfg& n, float* grad, const DwbcStorage* s, const int64_t* idx, int rows, const Plan& p, cudaStream_t st) {
+  const int Lld = (int)align_up(p.latent, 4);
+  const BwdDescs d = bwd_descs(n, p);
+  const int cnb = n.n_critic_layers, ctd = n.critic_dims[cnb - 1];
+  const int anb = n.n_actor_layers, atd = n.actor_dims[anb - 1];
+  const int in0 = n.num_prop + p.latent, np = n.n_priv_layers;
+  float* z = p.priv[np - 1];
   RowMat obs_all = rowmat_gather(s->observations, idx, s->obs_stride);
   WGroupBuilder wb;
-  head_wgrad(wb, grad, cl, rowmat(p.cb[cnb - 1], ctd), ctd);
-  head_wgrad(wb, grad, ca, rowmat(p.cb[cnb - 1], ctd), ctd);
+  head_wgrad(wb, grad, d.cl, rowmat(p.cb[cnb - 1], ctd), ctd);
+  head_wgrad(wb, grad, d.ca, rowmat(p.cb[cnb - 1], ctd), ctd);
   for (int l = cnb - 1; l >= 0; --l) {
     const int in = l == 0 ? n.num_prop + n.num_priv : n.critic_dims[l - 1];
     wb.add(rowmat(p.dzc_b[l], n.critic_dims[l]), l == 0 ? obs_all : rowmat(p.cb[l - 1], in), grad + n.off_critic_w[l], in, grad + n.off_critic_b[l],
            n.critic_dims[l], in);
   }
-  head_wgrad(wb, grad, al, rowmat(p.ab[anb - 1], atd), atd);
-  head_wgrad(wb, grad, aa, rowmat(p.ab[anb - 1], atd), atd);
+  head_wgrad(wb, grad, d.al, rowmat(p.ab[anb - 1], atd), atd);
+  head_wgrad(wb, grad, d.aa, rowmat(p.ab[anb - 1], atd), atd);
   for (int l = anb - 1; l >= 1; --l)
     wb.add(rowmat(p.dza_b[l], n.actor_dims[l]), rowmat(p.ab[l - 1], n.actor_dims[l - 1]), grad + n.off_actor_w[l], n.actor_dims[l - 1],
            grad + n.off_actor_b[l], n.actor_dims[l], n.actor_dims[l - 1]);
@@ -643,8 +672,7 @@ static int backward_chains(const DwbcNetCfg& n, const float* P, float* grad, con
     wb.add(rowmat(p.dzp[l], (int)align_up(n.priv_dims[l], 4)), X, grad + n.off_priv_w[l], in, grad + n.off_priv_b[l], n.priv_dims[l], in);
   }
   if (!wb.ok) return DWBC_ERR_UNSUPPORTED;
-  TRY(launch_wgrad_group(wb.g, rows, st));
-  return DWBC_OK;
+  return launch_wgrad_group(wb.g, rows, mlp_precision == 2, st);
 }
 
 }  // namespace dwbc
@@ -656,9 +684,17 @@ extern "C" int64_t dwbc_workspace_bytes(const DwbcNetCfg* net, int64_t rows) {
   return make_plan(*net, rows, nullptr).bytes;
 }
 
+// FinArgs of the rollout hooks
+static FinArgs fin_rollout(const DwbcNetCfg& n, const float* P, const float* eps, float* actions, float* log_prob, float* mean, float* sigma, int rows) {
+  FinArgs f{};
+  f.std = P + n.off_std; f.eps = eps; f.actions = actions; f.log_prob = log_prob; f.mean_out = mean; f.sigma_out = sigma;
+  f.n_leg = n.n_leg; f.n_act = n.n_leg + n.n_arm; f.rows = rows;
+  return f;
+}
+
 extern "C" int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, const float* eps,
                                int32_t hist_encoding, float* actions, float* values, float* log_prob, float* mean, float* sigma,
-                               int32_t rows, void* workspace, dwbc_stream_t stream) {
+                               int32_t rows, int32_t weights_packed, void* workspace, dwbc_stream_t stream) {
   TRY(check_net(net));
   if (!params || !obs || !eps || !actions || !values || !log_prob || !mean || !sigma || !workspace || rows <= 0) return DWBC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -668,18 +704,24 @@ extern "C" int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const
   int zld = (int)align_up(p.latent, 4);
   if (chain_usable(n, p, obs, obs_stride)) {
     if (hist_encoding) TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
-    TRY(forward_chains(n, params, obs, nullptr, obs_stride, rows, hist_encoding ? p.zh : nullptr, zld, p, values, getenv("DWBC_CHAIN_STORE") != nullptr /* profiling aid */, true, true, st));
-  } else {
-    if (hist_encoding) {
-      TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
-      z = p.zh;
-    } else {
-      TRY(priv_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
-      z = p.priv[n.n_priv_layers - 1];
-    }
-    TRY(actor_forward(n, params, obs, nullptr, obs_stride, rows, z, zld, p, st));
-    TRY(critic_forward(n, params, obs, nullptr, obs_stride, rows, p, values, st));
+    C2PackList pl{};
+    pl.out = p.wpack;
+    int64_t off = 0;
+    const bool x3 = mlp_precision == 2;
+    C2Builder A(&pl, &off, rows, x3), C(&pl, &off, rows, x3);
+    TRY(build_forward(n, params, obs, nullptr, obs_stride, hist_encoding ? p.zh : nullptr, zld, p, values, false, 1, &A, &C));
+    if (!weights_packed) TRY(launch_pack2(pl, st));       // the images stay valid in the workspace until the parameters change
+    return launch_chain2(&A.pr, &C.pr, fin_rollout(n, params, eps, actions, log_prob, mean, sigma, rows), x3, p.queue, st);
   }
+  if (hist_encoding) {
+    TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+    z = p.zh;
+  } else {
+    TRY(priv_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+    z = p.priv[n.n_priv_layers - 1];
+  }
+  TRY(actor_forward(n, params, obs, nullptr, obs_stride, rows, z, zld, p, st));
+  TRY(critic_forward(n, params, obs, nullptr, obs_stride, rows, p, values, st));
   act_finalize_kernel<<<(rows + 127) / 128, 128, 0, st>>>(p.mean, p.mean_ld, params + n.off_std, eps, actions, log_prob, mean, sigma, rows,
                                                            n.n_leg, n.n_leg + n.n_arm);
   DWBC_LAUNCH_CHECK();
@@ -690,10 +732,19 @@ extern "C" int dwbc_critic_values(const DwbcNetCfg* net, const float* params, co
                                   int32_t rows, void* workspace, dwbc_stream_t stream) {
   TRY(check_net(net));
   if (!params || !obs || !values || !workspace || rows <= 0) return DWBC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
   Plan p = make_plan(*net, rows, workspace);
-  if (chain_usable(*net, p, obs, obs_stride))
-    return forward_chains(*net, params, obs, nullptr, obs_stride, rows, nullptr, 0, p, values, false, false, true, (cudaStream_t)stream);
-  return critic_forward(*net, params, obs, nullptr, obs_stride, rows, p, values, (cudaStream_t)stream);
+  if (chain_usable(*net, p, obs, obs_stride)) {
+    C2PackList pl{};
+    pl.out = p.wpack;
+    int64_t off = 0;
+    const bool x3 = mlp_precision == 2;
+    C2Builder C(&pl, &off, rows, x3);
+    TRY(build_forward(*net, params, obs, nullptr, obs_stride, nullptr, 0, p, values, false, 0, nullptr, &C));
+    TRY(launch_pack2(pl, st));                              // (overwrites the images a previous dwbc_policy_act left behind)
+    return launch_chain2(&C.pr, nullptr, FinArgs{}, x3, p.queue, st);
+  }
+  return critic_forward(*net, params, obs, nullptr, obs_stride, rows, p, values, st);
 }
 
 extern "C" int dwbc_hist_latent(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, float* out, int64_t ld_out,
@@ -725,12 +776,33 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   float* z = p.priv[n.n_priv_layers - 1];
   if (!s->hist_latent) TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));           // PPO:175-176 (no grad)
   if (chain_usable(n, p, s->observations, s->obs_stride)) {
-    TRY(forward_chains(n, P, s->observations, idx, s->obs_stride, rows, nullptr, Lld, p, p.value, true, true, true, st));
-  } else {
-    TRY(priv_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));
-    TRY(actor_forward(n, P, s->observations, idx, s->obs_stride, rows, z, Lld, p, st));
-    TRY(critic_forward(n, P, s->observations, idx, s->obs_stride, rows, p, p.value, st));
+    // tensor-core path: forward chains with the loss in the heads' epilogues, backward chains, grouped weight gradients.  The
+    // weight images of all four programs are packed by ONE launch (the parameters are constant within a mini-batch).
+    C2PackList pl{};
+    pl.out = p.wpack;
+    int64_t off = 0;
+    const bool x3 = mlp_precision == 2;
+    C2Builder A(&pl, &off, rows, x3), C(&pl, &off, rows, x3), Ab(&pl, &off, rows, x3), Cb(&pl, &off, rows, x3);
+    TRY(build_forward(n, P, s->observations, idx, s->obs_stride, nullptr, Lld, p, p.value, true, 2, &A, &C));
+    TRY(build_backward(n, P, p, Ab, Cb));
+    if (off > C2_PACK_FLOATS) return DWBC_ERR_UNSUPPORTED;
+    FinArgs f{};
+    f.std = P + n.off_std; f.idx = idx; f.s_actions = s->actions; f.old_logp = s->log_prob; f.old_values = s->values; f.returns = s->returns;
+    f.adv = s->advantages;
+    f.zh = s->hist_latent ? s->hist_latent : p.zh; f.zh_ld = s->hist_latent ? s->hist_latent_ld : Lld; f.zh_by_src = s->hist_latent ? 1 : 0;
+    f.g_leg = p.g_leg; f.gleg_ld = gleg_ld; f.g_arm = p.g_arm; f.garm_ld = garm_ld; f.g_v = p.g_vl; f.gv_ld = 4; f.g_z = p.g_z; f.gz_ld = Lld;
+    f.grad_std = grad + n.off_std; f.losses = losses_out;
+    f.n_leg = n.n_leg; f.n_act = n.n_leg + n.n_arm; f.latent = p.latent; f.rows = rows;
+    f.clip = hp->clip_param; f.c_value = hp->value_loss_coef; f.c_ent = hp->entropy_coef; f.c_reg = hp->priv_reg_coef; f.rho = hp->mixing_ratio;
+    f.clipped_value = hp->use_clipped_value_loss;
+    TRY(launch_pack2(pl, st));
+    TRY(launch_chain2(&A.pr, &C.pr, f, x3, p.queue, st));
+    TRY(launch_chain2(&Ab.pr, &Cb.pr, FinArgs{}, x3, p.queue, st));
+    return weight_gradients(n, grad, s, idx, rows, p, st);
   }
+  TRY(priv_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));
+  TRY(actor_forward(n, P, s->observations, idx, s->obs_stride, rows, z, Lld, p, st));
+  TRY(critic_forward(n, P, s->observations, idx, s->obs_stride, rows, p, p.value, st));
 
   LossArgs a{};
   a.mean = p.mean; a.mean_ld = p.mean_ld; a.std = P + n.off_std; a.value = p.value; a.zp = z; a.zld = Lld; a.zh = s->hist_latent ? s->hist_latent : p.zh; a.zh_ld = s->hist_latent ? s->hist_latent_ld : Lld; a.zh_by_src = s->hist_latent ? 1 : 0;
@@ -743,7 +815,6 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   ppo_loss_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a);
   DWBC_LAUNCH_CHECK();
 
-  if (chain_usable(n, p, s->observations, s->obs_stride) && !getenv("DWBC_NO_BWD_CHAIN")) return backward_chains(n, P, grad, s, idx, rows, p, st);
   // ---- critic backward ----
   {
     const int nb = n.n_critic_layers, tdim = n.critic_dims[nb - 1];
@@ -860,22 +931,12 @@ extern "C" int dwbc_dagger_minibatch_grad(const DwbcNetCfg* net, const float* pa
   return DWBC_OK;
 }
 
-// 0 = fp32 CUDA-core GEMMs (default, parity anchor), 1 = TF32 tcgen05 GEMMs
-extern "C" int dwbc_set_mlp_precision(int mode) {
-  if (mode != 0 && mode != 1) return DWBC_ERR_ARG;
-  mlp_precision = mode;
-  tc_simple = getenv("DWBC_TC_SIMPLE") ? 1 : 0;
-  return DWBC_OK;
-}
-
 // Debug / test entry: one GEMM of the selected implementation on plain row-major device matrices.
 //   mode 0: Y[M,N] = act(X[M,K] W[N,K]^T + b)      mode 1: dX[M,N] = G[M,K] W[K,N]      mode 2: dW[M,N] += G[K,M]^T X[K,N], db += colsum(G)
 extern "C" int dwbc_debug_gemm(int mode, int tc, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc,
                                const float* bias, float* dbias, int M, int N, int K, int act, dwbc_stream_t stream) {
   const int saved = mlp_precision;
   mlp_precision = tc;
-  tc_simple = getenv("DWBC_TC_SIMPLE") ? 1 : 0;
-  tc_debug = getenv("DWBC_TC_DEBUG") ? atoi(getenv("DWBC_TC_DEBUG")) : 0;
   int rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0) rc = linear_fwd(rowmat(A, lda), Bm, ldb, bias, C, ldc, M, N, K, act, 0, st);

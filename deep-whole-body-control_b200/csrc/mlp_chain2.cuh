@@ -26,7 +26,7 @@
 
 namespace dwbc {
 
-constexpr int C2_MAX_OPS = 12, C2_MAX_LOADS = 6, C2_MAX_PACK = 26;
+constexpr int C2_MAX_OPS = 12, C2_MAX_LOADS = 6, C2_MAX_PACK = 36;   // pack items of one launch: forward + backward programs of both networks
 constexpr int C2_TILE = 128 * 128;                       // floats per operand tile
 constexpr int C2_WORKERS = 16;                           // epilogue / load warps: lane quarter = warp % 4, column group = warp / 4
 constexpr int C2_THREADS = 32 * (C2_WORKERS + 1);        // + the MMA warp (warp 16)
@@ -94,8 +94,6 @@ struct C2Launch {
 struct C2PackSeg { int kdst, ksrc, len; };
 struct C2PackItem { const float* w; int64_t ldw; const float* bias; int N, npad, kpad, transpose, nseg; C2PackSeg seg[2]; int64_t dst, dst_lo; };
 struct C2PackList { int n; float* out; C2PackItem it[C2_MAX_PACK]; };
-
-__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __global__ void pack_weights2_kernel(const __grid_constant__ C2PackList pl) {
   const C2PackItem& it = pl.it[blockIdx.y];
@@ -171,14 +169,11 @@ constexpr float C2_LOG_SQRT_2PI = 0.91893853320467274178f;
 
 template <int kAct>
 __device__ __forceinline__ void c2_bias_act(float* v, const float* bias, int nvalid) {
-  if (kAct == ACT_TANH) {                 // narrow output heads only: skip the columns beyond N
-    for (int jj = 0; jj < 32; ++jj) v[jj] = jj < nvalid ? t2_tanh(v[jj] + bias[jj]) : 0.0f;
-    return;
-  }
 #pragma unroll
   for (int jj = 0; jj < 32; ++jj) {
     float x = v[jj] + bias[jj];
     if (kAct == ACT_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;
+    if (kAct == ACT_TANH) x = t2_tanh(x);
     v[jj] = jj < nvalid ? x : 0.0f;
   }
 }
@@ -189,14 +184,17 @@ __device__ __forceinline__ void c2_fin_act(const FinArgs& f, int c, int64_t m, b
   if (!on) return;
   const int off = c == 0 ? 0 : f.n_leg, cnt = c == 0 ? f.n_leg : f.n_act - f.n_leg;
   float lp = 0.0f;
-  for (int i = 0; i < cnt; ++i) {
-    const float mu = v[i], sg = f.std[off + i];
-    const float a = mu + sg * f.eps[m * f.n_act + off + i];
-    const float d = a - mu;
-    lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
-    f.actions[m * f.n_act + off + i] = a;
-    f.mean_out[m * f.n_act + off + i] = mu;
-    f.sigma_out[m * f.n_act + off + i] = sg;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {            // compile-time indices keep v[] in registers
+    if (i < cnt) {
+      const float mu = v[i], sg = f.std[off + i];
+      const float a = mu + sg * f.eps[m * f.n_act + off + i];
+      const float d = a - mu;
+      lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
+      f.actions[m * f.n_act + off + i] = a;
+      f.mean_out[m * f.n_act + off + i] = mu;
+      f.sigma_out[m * f.n_act + off + i] = sg;
+    }
   }
   f.log_prob[2 * m + c] = lp;
 }
@@ -211,10 +209,13 @@ __device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, b
     src = f.idx ? f.idx[m] : m;
     const float* act = f.s_actions + src * f.n_act + off;
     float lp = 0.0f;
-    for (int i = 0; i < cnt; ++i) {
-      const float sg = f.std[off + i], d = act[i] - v[i];
-      lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
-      l_ent += 0.5f + C2_LOG_SQRT_2PI + logf(sg);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < cnt) {
+        const float sg = f.std[off + i], d = act[i] - v[i];
+        lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
+        l_ent += 0.5f + C2_LOG_SQRT_2PI + logf(sg);
+      }
     }
     const float a0 = f.adv[2 * src], a1 = f.adv[2 * src + 1];
     const float mix = c == 0 ? a0 + f.rho * a1 : a1 + f.rho * a0;                   // PPO:199-201
@@ -230,23 +231,29 @@ __device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, b
     glp = inv2m * g * ratio;
     float* grow = c == 0 ? f.g_leg + m * f.gleg_ld : f.g_arm + m * f.garm_ld;
     const int gld = c == 0 ? f.gleg_ld : f.garm_ld;
-    for (int i = 0; i < gld; ++i) {
-      float gm = 0.0f;
-      if (i < cnt) {
-        const float sg = f.std[off + i], d = act[i] - v[i];
-        gm = glp * d / (sg * sg) * (1.0f - v[i] * v[i]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < gld) {
+        float gm = 0.0f;
+        if (i < cnt) {
+          const float sg = f.std[off + i], d = act[i] - v[i];
+          gm = glp * d / (sg * sg) * (1.0f - v[i] * v[i]);
+        }
+        grow[i] = gm;
       }
-      grow[i] = gm;
     }
   }
-  for (int i = 0; i < cnt; ++i) {              // gradient of std: one atomic per warp and column
-    float gs = 0.0f;
-    if (on) {
-      const float sg = f.std[off + i], d = f.s_actions[src * f.n_act + off + i] - v[i];
-      gs = glp * ((d * d) / (sg * sg * sg) - 1.0f / sg) - f.c_ent * inv2m / sg;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {               // gradient of std: one atomic per warp and column
+    if (i < cnt) {                             // (warp-uniform)
+      float gs = 0.0f;
+      if (on) {
+        const float sg = f.std[off + i], d = f.s_actions[src * f.n_act + off + i] - v[i];
+        gs = glp * ((d * d) / (sg * sg * sg) - 1.0f / sg) - f.c_ent * inv2m / sg;
+      }
+      gs = warp_sum(gs);
+      if (lane == 0) atomicAdd(f.grad_std + off + i, gs);
     }
-    gs = warp_sum(gs);
-    if (lane == 0) atomicAdd(f.grad_std + off + i, gs);
   }
   const float ss = warp_sum(l_surr * inv2m), se = warp_sum(l_ent * inv2m);
   if (lane == 0) { atomicAdd(f.losses + 0, ss); atomicAdd(f.losses + 3, se); }
@@ -285,10 +292,14 @@ __device__ __forceinline__ void c2_fin_reg(const FinArgs& f, int64_t m, bool on,
   if (on) {
     const int64_t src = f.idx ? f.idx[m] : m;
     const float* zhr = f.zh + (f.zh_by_src ? src : m) * f.zh_ld;
-    for (int i = 0; i < f.latent; ++i) { const float d = v[i] - zhr[i]; nrm += d * d; }
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < f.latent) { const float d = v[i] - zhr[i]; nrm += d * d; }
     nrm = sqrtf(nrm);
     const float s = nrm > 0.0f ? f.c_reg * invm / nrm : 0.0f;
-    for (int i = 0; i < f.gz_ld; ++i) f.g_z[m * f.gz_ld + i] = i < f.latent ? s * (v[i] - zhr[i]) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < f.gz_ld) f.g_z[m * f.gz_ld + i] = i < f.latent ? s * (v[i] - zhr[i]) : 0.0f;
   }
   const float s = warp_sum(nrm * invm);
   if (lane == 0) atomicAdd(f.losses + 2, s);
@@ -531,6 +542,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
                 for (int j4 = 0; j4 < 8; ++j4)
                   if (c0 + 4 * j4 < o.N) *reinterpret_cast<float4*>(yr + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
               } else {
+#pragma unroll
                 for (int jj = 0; jj < 32; ++jj)
                   if (c0 + jj < o.N) yr[jj] = v[jj];
               }
@@ -586,7 +598,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
 
 // ---- host side ------------------------------------------------------------------------------------------------------
 inline bool c2_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-constexpr int64_t C2_PACK_FLOATS = (int64_t)4 * C2_MAX_PACK * (C2_TILE + 256);      // forward + backward lists, raw + low images
+constexpr int64_t C2_PACK_FLOATS = (int64_t)2 * C2_MAX_PACK * (C2_TILE + 256);      // raw + low images of every item
 
 inline int launch_pack2(const C2PackList& pl, cudaStream_t st) {
   if (pl.n <= 0) return DWBC_OK;

@@ -24,11 +24,18 @@ struct WGItem {
 };
 struct WGroup { int n, rows, slab, nslab; WGItem it[WG_MAX]; };
 
+// X3 = error-compensated mode (3xTF32): a stage additionally holds the low parts G_lo = G - trunc_tf32(G), X_lo of its two
+// operand tiles (the tensor core truncates the 13 low mantissa bits of the raw tiles itself), chunks are 32 rows instead of 64 so
+// that three stages still fit, and every chunk is three accumulating MMA groups: G^T X + G_lo^T X + G^T X_lo.  The thread that
+// copied a 16-byte piece also splits it (after cp.async.wait_group), one chunk behind its copies.
+template <bool X3>
 __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid_constant__ WGroup grp) {
   extern __shared__ __align__(1024) float wg_smem[];
   __shared__ T2Shared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int TILE = T2_WCH * 128;                // floats per operand tile: 64 rows x 128 features
+  constexpr int WCH = X3 ? 32 : T2_WCH;             // rows per chunk
+  constexpr int TILE = WCH * 128;                   // floats per operand tile: WCH rows x 128 features
+  constexpr int STAGE = (X3 ? 4 : 2) * TILE;        // {G, X} or {G, X, G_lo, X_lo}
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
       tc_mbar_init(&sh.full[i], T2_PROD + T2_EPI);
@@ -45,17 +52,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
   const int items = grp.n * grp.nslab;
   const int my_items = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
+  // byte offset of the 16-byte piece (row k, piece c4) inside an operand tile (SWIZZLE_128B_BASE32B, MN-major)
+  auto piece_off = [](int k, int c4) -> uint32_t {
+    return (uint32_t)((c4 >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((c4 >> 1) & 3) ^ (k & 3)) << 5) + ((c4 & 1) << 4));
+  };
   // chunk `cc` is the CTA-wide running chunk counter (stage cc % 3, use cc / 3): identical in every thread
   auto fill_chunk = [&](const WGItem& g, int64_t k0, int nk, uint32_t cc, int pt) {
     const int s = cc % 3;
     asm volatile("bar.sync 4, 256;" ::: "memory");      // row-offset table of the previous chunk no longer read (and, at an item
                                                         // boundary, the epilogue has released the stages it used as staging)
-    if (pt < T2_WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
-    else if (pt < 2 * T2_WCH) sh.rowoff[pt] = (pt - T2_WCH) < nk ? (g.X.row(k0 + pt - T2_WCH) - g.X.p) : 0;
+    if (pt < WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
+    else if (pt >= 64 && pt < 64 + WCH) sh.rowoff[pt] = (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
     tc_mbar_wait(&sh.empty[s], ((cc / 3) & 1) ^ 1);
     asm volatile("bar.sync 4, 256;" ::: "memory");
     for (int op = 0; op < 2; ++op) {
-      float* dst = wg_smem + (2 * s + op) * TILE;
+      float* dst = wg_smem + s * STAGE + op * TILE;
       const float* base = op == 0 ? g.G.p : g.X.p;
       const int64_t* ro = sh.rowoff + 64 * op;
       const int ncol = op == 0 ? g.Mo : g.Ni;
@@ -64,21 +75,66 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
         const uint32_t d0 = tc_smem_u32(dst);
         const bool pow2 = (cpr & (cpr - 1)) == 0;
         const int sh2 = 31 - __clz(cpr);
-        for (int i = pt; i < T2_WCH * cpr; i += 256) {
+        for (int i = pt; i < WCH * cpr; i += 256) {
           const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;          // row, piece
           const float* src = k < nk ? base + ro[k] + 4 * c4 : base;
-          const uint32_t off = (uint32_t)((c4 >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((c4 >> 1) & 3) ^ (k & 3)) << 5) + ((c4 & 1) << 4));
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + off), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + piece_off(k, c4)), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
         }
       } else {
-        for (int i = pt; i < T2_WCH * ncol; i += 256) {
+        for (int i = pt; i < WCH * ncol; i += 256) {
           const int k = i / ncol, f = i - k * ncol;
           const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
           dst[off] = k < nk ? base[ro[k] + f] : 0.0f;
         }
       }
     }
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.full[s])) : "memory");
+    if (!X3) asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.full[s])) : "memory");
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // X3: low parts of the pieces this thread copied into stage cc % 3 (its copies have landed: cp.async.wait_group before the call)
+  auto split_chunk = [&](const WGItem& g, uint32_t cc, int pt) {
+    const int s = cc % 3;
+    for (int op = 0; op < 2; ++op) {
+      float* src = wg_smem + s * STAGE + op * TILE;
+      float* dst = src + 2 * TILE;
+      const int ncol = op == 0 ? g.Mo : g.Ni;
+      if (op == 0 ? g.fastG : g.fastX) {
+        const int cpr = ncol >> 2;
+        const bool pow2 = (cpr & (cpr - 1)) == 0;
+        const int sh2 = 31 - __clz(cpr);
+        for (int i = pt; i < WCH * cpr; i += 256) {
+          const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;
+          const uint32_t off = piece_off(k, c4) >> 2;
+          const float4 v = *reinterpret_cast<const float4*>(src + off);
+          *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+      } else {
+        for (int i = pt; i < WCH * ncol; i += 256) {
+          const int k = i / ncol, f = i - k * ncol;
+          const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
+          dst[off] = tf32_lo(src[off]);
+        }
+      }
+    }
+    tc_fence_async_smem();
+    t2_arrive(&sh.full[s]);
+  };
+  // the fill schedule of one item for a filling thread: plain mode = fill every chunk (asynchronous arrival); X3 = copies run one
+  // chunk ahead of the split
+  auto fill_item = [&](const WGItem& g, int64_t k_begin, int64_t k_end, int nch, uint32_t cc, int pt, auto&& between) {
+    for (int c = 0; c < nch; ++c) {
+      const int64_t k0 = k_begin + (int64_t)c * WCH;
+      fill_chunk(g, k0, (int)min((int64_t)WCH, k_end - k0), cc + c, pt);
+      if (X3 && c > 0) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        split_chunk(g, cc + c - 1, pt);
+      }
+      between(c);
+    }
+    if (X3 && nch > 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      split_chunk(g, cc + nch - 1, pt);
+    }
   };
 
   uint32_t cc = 0;                                     // running chunk counter
@@ -87,13 +143,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
     const WGItem& g = grp.it[w % grp.n];
     const int64_t k_begin = (int64_t)(w / grp.n) * grp.slab;
     const int64_t k_end = min((int64_t)grp.rows, k_begin + grp.slab);
-    const int nch = (int)((k_end - k_begin + T2_WCH - 1) / T2_WCH);
+    const int nch = (int)((k_end - k_begin + WCH - 1) / WCH);
     const int Mo = g.Mo, Ni = g.Ni, nipad = (Ni + 15) & ~15;
     if (warp < 4) {
-      for (int c = 0; c < nch; ++c) {
-        const int64_t k0 = k_begin + (int64_t)c * T2_WCH;
-        fill_chunk(g, k0, (int)min((int64_t)T2_WCH, k_end - k0), cc + c, tid);
-      }
+      fill_item(g, k_begin, k_end, nch, cc, tid, [](int) {});
     } else if (warp == 4) {
       if (lane == 0) {
         const uint32_t idesc = tc_idesc(nipad, true, true);
@@ -103,11 +156,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
           tc_mbar_wait(&sh.full[s], (u / 3) & 1);
           tc_fence_async_smem();          // generic-proxy writes of the producers (made visible by the barrier) -> async proxy reads of the MMA
           tc_fence_after();
-          const uint32_t a0 = tc_smem_u32(wg_smem + (2 * s) * TILE), b0 = a0 + TILE * 4;
-          for (int kk = 0; kk < T2_WCH; kk += 8) {
+          const uint32_t a0 = tc_smem_u32(wg_smem + s * STAGE), b0 = a0 + TILE * 4;
+          for (int kk = 0; kk < WCH; kk += 8) {
             const uint64_t ad = tc_desc(a0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
             const uint64_t bd = tc_desc(b0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
             tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+            if (X3) {
+              const uint64_t adl = tc_desc(a0 + 2 * TILE * 4 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
+              const uint64_t bdl = tc_desc(b0 + 2 * TILE * 4 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
+              tc_mma_tf32(tmem, adl, bd, idesc, 1u);
+              tc_mma_tf32(tmem, ad, bdl, idesc, 1u);
+            }
           }
           tc_commit(&sh.empty[s]);
         }
@@ -122,21 +181,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
       auto bias_chunk = [&](uint32_t u) {
         const int s = u % 3;
         tc_mbar_wait(&sh.full[s], (u / 3) & 1);
-        const float* gt = wg_smem + (2 * s) * TILE;
+        const float* gt = wg_smem + s * STAGE;
         if (g.db != nullptr && et < Mo) {
 #pragma unroll 8
-          for (int k = 0; k < T2_WCH; ++k) bsum += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
+          for (int k = 0; k < WCH; ++k) bsum += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
         }
         __syncwarp();
         if (lane == 0) t2_arrive(&sh.empty[s]);
       };
-      for (int c = 0; c < nch; ++c) {
-        const int64_t k0 = k_begin + (int64_t)c * T2_WCH;
-        fill_chunk(g, k0, (int)min((int64_t)T2_WCH, k_end - k0), cc + c, T2_PROD + et);
-        if (c > 0) bias_chunk(cc + c - 1);
-      }
+      // bias sums of chunk c-1 right after the copies of chunk c were issued (X3: and chunk c-1 was split)
+      int done = 0;                                     // chunks whose bias sums are taken
+      fill_item(g, k_begin, k_end, nch, cc, T2_PROD + et, [&](int c) {
+        while (done < c) { bias_chunk(cc + done); ++done; }      // chunks 0 .. c-1 have been handed over by this thread
+      });
+      while (done < nch) { bias_chunk(cc + done); ++done; }
       if (nch > 0) {
-        bias_chunk(cc + nch - 1);
         if (g.db && et < Mo) atomicAdd(g.db + et, bsum);
         const int o = q * 32 + lane;
         tc_mbar_wait(&sh.tfull[0], j & 1);
@@ -187,7 +246,7 @@ struct WGroupBuilder {
   }
 };
 
-inline int launch_wgrad_group(WGroup& g, int rows, cudaStream_t st) {
+inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
   if (g.n <= 0 || rows <= 0) return DWBC_ERR_ARG;
   static int sms = 0;
   if (!sms) {
@@ -197,12 +256,11 @@ inline int launch_wgrad_group(WGroup& g, int rows, cudaStream_t st) {
   }
   g.rows = rows;
   // slab length: ~4 work items per CTA, at least 4 chunks so that the epilogue stays amortised
-  static int per_cta = 0;                              // work items per CTA (tuning knob: DWBC_WG_ITEMS)
-  if (!per_cta) { const char* e = getenv("DWBC_WG_ITEMS"); per_cta = e ? atoi(e) : 4; if (per_cta < 1) per_cta = 4; }
+  constexpr int per_cta = 4;                           // work items per CTA
   int64_t total_items = (int64_t)per_cta * sms;
   int64_t nslab = (total_items + g.n - 1) / g.n;
   int64_t slab = (rows + nslab - 1) / nslab;
-  slab = (slab + T2_WCH - 1) / T2_WCH * T2_WCH;
+  slab = (slab + T2_WCH - 1) / T2_WCH * T2_WCH;          // (a multiple of the 32-row chunks of the 3xTF32 mode too)
   if (slab < 4 * T2_WCH) slab = 4 * T2_WCH;
   g.slab = (int)slab;
   g.nslab = (int)((rows + slab - 1) / slab);
@@ -211,10 +269,13 @@ inline int launch_wgrad_group(WGroup& g, int rows, cudaStream_t st) {
   const size_t smem = (size_t)(6 * T2_WCH * 128) * sizeof(float);       // 3 stages x {G tile, X tile} = 192 KB (>= the 66 KB staging tile)
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DWBC_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(wgrad_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(wgrad_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return DWBC_ERR_LAUNCH;
     attr = true;
   }
-  wgrad_group_kernel<<<grid, T2_THREADS, smem, st>>>(g);
+  if (x3) wgrad_group_kernel<true><<<grid, T2_THREADS, smem, st>>>(g);
+  else wgrad_group_kernel<false><<<grid, T2_THREADS, smem, st>>>(g);
   ++dwbc_launch_counter;
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }

@@ -77,8 +77,7 @@ class FusedPPO:
         self.counter = 0
         self.world_size, self.process_group = world_size, process_group
         self._zh_all = None
-        if precision not in ("fp32", "tf32"):
-            raise L.DwbcError("precision must be 'fp32' (CUDA-core GEMMs, parity anchor) or 'tf32' (tcgen05 tensor cores)")
+        self._packed = False          # tensor-core weight images in the workspace match the current parameters (rollout reuse)
         self.precision = precision
         ac = actor_critic
         self.optimizer = _AdamState(ac, 0, ac.num_params, learning_rate)                  # PPO:75
@@ -105,8 +104,26 @@ class FusedPPO:
                         [torch.zeros(num_envs, 2, device=self.device) for _ in range(2)]
         self._workspace(max(num_envs, num_envs * num_transitions_per_env // self.num_mini_batches))
 
+    @property
+    def precision(self):
+        return self._precision
+
+    @precision.setter
+    def precision(self, value):
+        """'fp32' (CUDA-core GEMMs, parity anchor), 'tf32' (tcgen05, truncated 10-bit-mantissa operands) or 'tf32x3' (tcgen05,
+        error-compensated three-product split: fp32-grade).  Travels to the kernels per call inside DwbcNetCfg.precision."""
+        if value not in L.PRECISIONS:
+            raise L.DwbcError("precision must be one of " + ", ".join(L.PRECISIONS))
+        self._precision = value
+        self.actor_critic.net_cfg.precision = L.PRECISIONS[value]
+        self._packed = False
+
     def _set_precision(self):
-        L.check(self._lib.dwbc_set_mlp_precision(1 if self.precision == "tf32" else 0), "dwbc_set_mlp_precision")
+        self.actor_critic.net_cfg.precision = L.PRECISIONS[self._precision]
+
+    def params_changed(self):
+        """Call after writing `actor_critic.flat` from outside (load_state_dict does it): the cached weight images are stale."""
+        self._packed = False
 
     def _workspace(self, rows):
         if self._ws is None or rows > self._ws_rows:
@@ -148,9 +165,12 @@ class FusedPPO:
                 [torch.zeros(n, 2, device=self.device) for _ in range(2)]
             obs_c = obs.contiguous()
         ws = self._workspace(n)
+        key = (n, int(bool(hist_encoding)), ac.flat._version)
+        packed = self._packed and self._packed_key == key
         L.check(self._lib.dwbc_policy_act(C.addressof(ac.net_cfg), L.ptr(ac.flat), L.ptr(obs_c), obs_c.stride(0), L.ptr(eps),
                                           int(bool(hist_encoding)), L.ptr(acts), L.ptr(vals), L.ptr(lp), L.ptr(mu), L.ptr(sg), n,
-                                          L.ptr(ws), L.stream_ptr()), "dwbc_policy_act")
+                                          int(packed), L.ptr(ws), L.stream_ptr()), "dwbc_policy_act")
+        self._packed, self._packed_key = True, key
         tr = self.transition
         tr.actions, tr.values, tr.actions_log_prob, tr.action_mean, tr.action_sigma = acts, vals, lp, mu, sg
         tr.observations = tr.critic_observations = obs
@@ -178,6 +198,7 @@ class FusedPPO:
         L.check(self._lib.dwbc_critic_values(C.addressof(ac.net_cfg), L.ptr(ac.flat), L.ptr(obs), obs.stride(0),
                                              L.ptr(self._last_values), obs.shape[0], L.ptr(self._workspace(obs.shape[0])),
                                              L.stream_ptr()), "dwbc_critic_values")
+        self._packed = False                      # dwbc_critic_values re-packs the critic into the same workspace region
         s.compute_returns(self._last_values, self.gamma, self.lam, self.world_size, self.process_group)
 
     # ------------------------------------------------------------------ schedules (PPO:178-179, 301-302)
@@ -205,6 +226,7 @@ class FusedPPO:
     def update(self, indices=None, on_step=None):
         ac, s, hp = self.actor_critic, self.storage, self._fill_hp()
         self._set_precision()
+        self._packed = False                      # the parameters move (and the workspace is re-used with another row count)
         if indices is None:
             indices, _ = s.draw_indices(self.num_mini_batches, self.generator)
         indices = indices.to(torch.int64).contiguous()
@@ -252,6 +274,7 @@ class FusedPPO:
         """PPO:265-291."""
         ac, s, hp = self.actor_critic, self.storage, self._fill_hp()
         self._set_precision()
+        self._packed = False
         if indices is None:
             indices, _ = s.draw_indices(self.num_mini_batches, self.generator)
         indices = indices.to(torch.int64).contiguous()
@@ -278,5 +301,6 @@ class FusedPPO:
         if self.min_policy_std is None:
             return
         ac = self.actor_critic
+        self._packed = False
         L.check(self._lib.dwbc_enforce_min_std(L.ptr(ac.flat), ac.offsets["std"], L.ptr(self.min_policy_std),
                                                self.min_policy_std.numel(), L.stream_ptr()), "dwbc_enforce_min_std")

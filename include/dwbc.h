@@ -11,7 +11,7 @@
  *
  * Conventions: every pointer is a DEVICE pointer into a caller-owned, contiguous, row-major
  * buffer (fp32 unless the type says otherwise).  The library allocates nothing, keeps no
- * global state, never synchronises and never throws: every function enqueues its kernels on
+ * global state (except a launch counter), never synchronises and never throws: every function enqueues its kernels on
  * the given stream and returns DWBC_OK or a negative error code.  Structs are passed by
  * pointer to HOST memory and are read before the call returns.
  */
@@ -33,7 +33,7 @@ enum {
   DWBC_ERR_LAUNCH = -3       /* cudaGetLastError() != cudaSuccess after the launch */
 };
 
-#define DWBC_ABI_VERSION 1
+#define DWBC_ABI_VERSION 2
 #define DWBC_MAX_DOF 24
 #define DWBC_MAX_TERMS 40   /* active reward terms per channel */
 #define DWBC_MAX_IDX 8      /* penalised / termination contact bodies */
@@ -245,6 +245,13 @@ typedef struct DwbcNetCfg {
   int64_t off_critic_w[DWBC_MAX_LAYERS], off_critic_b[DWBC_MAX_LAYERS];
   int64_t off_cleg_w[DWBC_MAX_LAYERS + 1], off_cleg_b[DWBC_MAX_LAYERS + 1];
   int64_t off_carm_w[DWBC_MAX_LAYERS + 1], off_carm_b[DWBC_MAX_LAYERS + 1];
+  /* Arithmetic of the ActorCritic GEMMs, per call (no process-wide switch):
+   *   0  fp32 CUDA cores (parity anchor of the tests);
+   *   1  TF32 operands (10-bit mantissa, truncated), fp32 accumulation, tcgen05 tensor cores;
+   *   2  "3xTF32": every operand is split into the TF32 part the tensor core reads and the exact remainder, three tensor-core
+   *      products per GEMM (hi*hi + lo*hi + hi*lo), fp32 accumulation: fp32-grade results on the tensor cores. */
+  int32_t precision;
+  int32_t reserved_;
 } DwbcNetCfg;
 
 /* PD torque controller of step() (WG:1262-1295 `_compute_torques`, called `decimation` times per policy step, WG:1175-1183):
@@ -265,10 +272,13 @@ int64_t dwbc_workspace_bytes(const DwbcNetCfg* net, int64_t rows);
 
 /* PPO.act (PPO:115-127 = AC:337-353): obs[N,obs_stride] -> mean, sigma, actions = mean +
  * sigma*eps (eps[N,n_act] standard normal supplied by the caller), two-channel log-prob of the
- * action, critic values.  hist_encoding selects the history encoder latent (AC:207-210). */
+ * action, critic values.  hist_encoding selects the history encoder latent (AC:207-210).
+ * weights_packed: 0 = (re)build the tensor-core weight images in the workspace from `params`; 1 = reuse the images a previous
+ * call left in this workspace (same net, same rows, parameters unchanged since, no other entry point run on the workspace in
+ * between) -- lets a rollout pack once per iteration instead of once per step.  Ignored by the fp32 path. */
 int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, const float* eps,
                     int32_t hist_encoding, float* actions, float* values, float* log_prob, float* mean, float* sigma,
-                    int32_t rows, void* workspace, dwbc_stream_t stream);
+                    int32_t rows, int32_t weights_packed, void* workspace, dwbc_stream_t stream);
 
 /* critic only (PPO:148-150 last_values; AC:351-353) */
 int dwbc_critic_values(const DwbcNetCfg* net, const float* params, const float* obs, int64_t obs_stride, float* values,
@@ -313,10 +323,6 @@ int dwbc_dagger_minibatch_grad(const DwbcNetCfg* net, const float* params, const
 int dwbc_clip_adam_step(float* params, float* grad, float* adam_m, float* adam_v, int64_t first, int64_t count,
                         const DwbcPpoHyper* hp, int32_t step, double* norm_scratch, float* grad_norm_out,
                         dwbc_stream_t stream);
-
-/* Precision of the ActorCritic GEMMs: 0 = fp32 CUDA cores (default; parity anchor), 1 = TF32 inputs / fp32 accumulate
- * on the tcgen05 tensor cores. */
-int dwbc_set_mlp_precision(int mode);
 
 /* PPO.enforce_min_std (PPO:293-296): std = max(std, min_std). */
 int dwbc_enforce_min_std(float* params, int64_t off_std, const float* min_std, int32_t n, dwbc_stream_t stream);

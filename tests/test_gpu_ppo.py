@@ -76,11 +76,13 @@ def test_gae_matches_oracle_full_size(N, T):
     np.testing.assert_allclose(s.advantages.cpu().numpy(), adv.numpy(), rtol=1e-5, atol=2e-6)
 
 
-def test_policy_act_matches_reference_golden():
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_policy_act_matches_reference_golden(precision):
+    """fp32 tolerances for both the CUDA-core anchor and the error-compensated tensor-core path (3xTF32)."""
     g = np.load(os.path.join(G, "ppo.npz"))
     N, T, seed, _ = [int(x) for x in g["meta"]]
     P = golden_params(g, seed)
-    alg = make_alg(N, T, P)
+    alg = make_alg(N, T, P, precision=precision)
     inp = synth.rollout_inputs(N, T, 860, seed)
     obs = torch.from_numpy(inp["obs"]).cuda()
     for t in (0, 1, T - 1):
@@ -110,7 +112,7 @@ def test_policy_act_matches_reference_golden():
         k = Pd[n].numel()
         Pd[n] = flat20[off:off + k].view_as(Pd[n]).clone()
         off += k
-    alg2 = make_alg(N, T, Pd)
+    alg2 = make_alg(N, T, Pd, precision=precision)
     inp2 = synth.rollout_inputs(N, T, 860, seed + 1)
     o0 = torch.from_numpy(inp2["obs"][0]).cuda()
     eps2 = ((torch.from_numpy(g["dag_actions0"]) - torch.from_numpy(g["dag_mu0"])) / Pd["std"]).cuda()
@@ -128,15 +130,18 @@ def _flat_ref(ac, vec):
     return out
 
 
-def test_ppo_update_matches_reference_golden():
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_ppo_update_matches_reference_golden(precision):
     """BASELINE.json configs[0] on the GPU: losses, clipped gradient of step 1, post-Adam parameters
-    after step 1 and after the full 20-step update(), fp32 CUDA-core path.
+    after step 1 and after the full 20-step update().  The SAME fp32 tolerances hold for the CUDA-core anchor ('fp32') and for
+    the error-compensated tensor-core path ('tf32x3': fused chains + grouped weight gradients on tcgen05, three TF32 products
+    per GEMM) -- the path bench.py reports as its headline.
     Stated fp32 tolerances: clipped grads rtol 1e-3 / atol 2e-6; parameters atol 3e-6 after one Adam
     step (Adam's first update is lr*g/(|g|+eps): entries with |g| ~ eps=1e-8 amplify rounding, bounded
     by 2*lr = 4e-4) and atol 2e-5 after the full 20-step update()."""
     g = np.load(os.path.join(G, "ppo.npz"))
     N, T, seed, counter = [int(x) for x in g["meta"]]
-    alg = make_alg(N, T, golden_params(g, seed))
+    alg = make_alg(N, T, golden_params(g, seed), precision=precision)
     alg.counter = counter
     fill_storage(alg, g, synth.rollout_inputs(N, T, 860, seed), T)
     ac = alg.actor_critic
@@ -153,6 +158,9 @@ def test_ppo_update_matches_reference_golden():
     assert res[3] == ref[3] and abs(res[6] - ref[6]) < 1e-7
     g1, p1, p20 = _flat_ref(ac, g["grad1"]), _flat_ref(ac, g["param1"]), _flat_ref(ac, g["param20"])
     got_g, got_p1, got_p20 = ac.unflat(snap["grad1"]), ac.unflat(snap["param1"]), ac.unflat(ac.flat)
+    worst = [max(float((a[n].cpu() - b[n]).abs().max()) for n, _ in ac.manifest) for a, b in ((got_g, g1), (got_p1, p1), (got_p20, p20))]
+    print(f"[{precision}] max abs error vs the reference: clipped grad {worst[0]:.3g}, params after 1 step {worst[1]:.3g}, after 20 steps {worst[2]:.3g}; "
+          f"losses {res[0] - ref[0]:+.3g} {res[1] - ref[1]:+.3g} {res[5] - ref[5]:+.3g}")
     for n, _ in ac.manifest:
         np.testing.assert_allclose(got_g[n].cpu().numpy(), g1[n].numpy(), rtol=1e-3, atol=2e-6, err_msg="grad1 " + n)
         np.testing.assert_allclose(got_p1[n].cpu().numpy(), p1[n].numpy(), rtol=0, atol=3e-6, err_msg="param1 " + n)
@@ -224,11 +232,15 @@ def test_minibatch_grad_matches_oracle_autograd_large():
     assert abs(float(ls[2]) - float(info["priv_reg"])) < 1e-4
 
 
+# Tolerances of the plain TF32 path = 2 x the errors MEASURED on B200 against the reference golden vectors (printed by the test;
+# operands truncated to 10 mantissa bits by the tensor core, fp32 accumulation, up to 6 layers deep).  The bound on the parameters is on
+# the RMS, not the max: Adam's update is ~lr * sign(g) for small |g|, so one entry whose tiny gradient changes sign moves by up to 2*lr
+# per step whatever the precision of the rest; the RMS says how many entries do that.
+TF32_TOL = dict(mean=8e-3, value=8e-3, loss_rel=1e-2, grad_rel_norm=1e-2, param20_rms=4e-5, param20_max=4e-3)
+
+
 def test_tf32_tensor_core_path_matches_reference_within_stated_tolerance():
-    """precision='tf32' (tcgen05, 10-bit mantissa inputs, fp32 accumulate) on BASELINE configs[0].
-    Stated tolerances: forward values / means 2e-2 abs, mean losses 2 % relative, clipped step-1 gradient within 5 % of its
-    own norm (||dg|| / ||g||), parameters after the 20-step update() within 20 * lr = 4e-3 (Adam moves each entry by at
-    most ~lr per step, so a sign flip of a tiny gradient costs at most 2*lr per step)."""
+    """precision='tf32' (tcgen05, truncated 10-bit mantissa inputs, fp32 accumulate) on BASELINE configs[0] against the reference golden."""
     g = np.load(os.path.join(G, "ppo.npz"))
     N, T, seed, counter = [int(x) for x in g["meta"]]
     P = golden_params(g, seed)
@@ -238,8 +250,8 @@ def test_tf32_tensor_core_path_matches_reference_within_stated_tolerance():
     mean_o = PO.actor_mean(P, obs0.cpu())
     eps = ((torch.from_numpy(g["actions"][0]) - mean_o) / P["std"]).cuda()
     alg.act(obs0, obs0, False, eps=eps)
-    np.testing.assert_allclose(alg.storage.mu[0].cpu().numpy(), g["mu0"], rtol=0, atol=2e-2)
-    np.testing.assert_allclose(alg.storage.values[0].cpu().numpy(), g["values"][0], rtol=0, atol=2e-2)
+    e_mean = float(np.abs(alg.storage.mu[0].cpu().numpy() - g["mu0"]).max())
+    e_val = float(np.abs(alg.storage.values[0].cpu().numpy() - g["values"][0]).max())
     alg.storage.step = 0
     alg.counter = counter
     fill_storage(alg, g, inp, T)
@@ -252,20 +264,30 @@ def test_tf32_tensor_core_path_matches_reference_within_stated_tolerance():
 
     res = alg.update(indices=torch.from_numpy(g["perm"]).cuda().long(), on_step=on_step)
     ref = g["update_result"]
-    assert abs(res[0] - ref[0]) < 2e-2 * abs(ref[0]) and abs(res[1] - ref[1]) < 2e-3 and abs(res[5] - ref[5]) < 2e-2 * abs(ref[5])
     g1 = torch.cat([v.reshape(-1) for v in _flat_ref(ac, g["grad1"]).values()])
     got = torch.cat([v.reshape(-1).cpu() for v in ac.unflat(snap["grad1"]).values()])
-    assert float((got - g1).norm() / g1.norm()) < 5e-2
     p20 = torch.cat([v.reshape(-1) for v in _flat_ref(ac, g["param20"]).values()])
     gotp = torch.cat([v.reshape(-1).cpu() for v in ac.unflat(ac.flat).values()])
-    assert float((gotp - p20).abs().max()) < 4e-3
+    e_grad = float((got - g1).norm() / g1.norm())
+    e_rms, e_max = float((gotp - p20).pow(2).mean().sqrt()), float((gotp - p20).abs().max())
+    e_loss = max(abs(res[0] - ref[0]) / abs(ref[0]), abs(res[1] - ref[1]) / max(abs(ref[1]), 1e-3), abs(res[5] - ref[5]) / abs(ref[5]))
+    print(f"[tf32] measured: mean {e_mean:.3g}, value {e_val:.3g}, losses rel {e_loss:.3g}, clipped grad ||dg||/||g|| {e_grad:.3g}, "
+          f"params after 20 steps rms {e_rms:.3g} max {e_max:.3g}")
+    assert e_mean < TF32_TOL["mean"] and e_val < TF32_TOL["value"] and e_loss < TF32_TOL["loss_rel"]
+    assert e_grad < TF32_TOL["grad_rel_norm"]
+    assert e_rms < TF32_TOL["param20_rms"] and e_max < TF32_TOL["param20_max"]
 
 
+# forward: max abs difference of means / values to the exact-fp32 path; gradient: ||dg|| / ||g|| per parameter tensor
+CHAIN_TOL = {"tf32": dict(fwd=8e-3, grad=1e-2, loss=2e-3), "tf32x3": dict(fwd=2e-5, grad=2e-5, loss=2e-5)}
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("hist", [False, True])
-def test_fused_chain_forward_matches_fp32_path_many_tiles(hist):
-    """The fused layer-chain kernel (TF32, mlp_chain.cuh) against the exact-fp32 layer-wise path of the same library
-    (itself pinned to the reference by the tests above) at a row count that gives every CTA several tiles plus a ragged
-    last tile.  Stated tolerance: 2e-2 abs on means / values (TF32 inputs through up to 6 layers)."""
+def test_fused_chain_forward_matches_fp32_path_many_tiles(hist, precision):
+    """The fused layer-chain kernel (mlp_chain2.cuh; TF32 and error-compensated 3xTF32) against the exact-fp32 layer-wise path of the same
+    library (itself pinned to the reference by the tests above) at a row count that gives every CTA several tile pairs plus a ragged
+    last tile.  Tolerances: CHAIN_TOL (TF32: 2 x measured; 3xTF32: fp32-grade)."""
     g = np.load(os.path.join(G, "ppo.npz"))
     P = golden_params(g, int(g["meta"][2]))
     N = 148 * 128 * 2 + 3 * 128 + 77
@@ -273,23 +295,33 @@ def test_fused_chain_forward_matches_fp32_path_many_tiles(hist):
     obs = torch.randn(N, 860, device="cuda", generator=gen)
     eps = torch.randn(N, 18, device="cuda", generator=gen)
     out = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", precision):
         alg = make_alg(N, 1, P, precision=prec)
         alg.act(obs, obs, hist, eps=eps)
         s = alg.storage
         alg.compute_returns(obs)                                   # critic-only chain (PPO:148-150)
+        s.step = 0
+        alg.act(obs, obs, hist, eps=eps)                           # second call re-packs (compute_returns used the workspace), third reuses the images
+        first = s.mu[0].clone()
+        alg.act(obs, obs, hist, eps=eps)
+        assert torch.equal(first, s.mu[0])
         out[prec] = [s.mu[0].clone(), s.values[0].clone(), s.actions[0].clone(), s.actions_log_prob[0].clone(), alg._last_values.clone()]
+        assert torch.equal(s.sigma[0], alg.actor_critic.std.expand(N, -1))
         del alg
-    for a, b in zip(out["fp32"][:3] + out["fp32"][4:], out["tf32"][:3] + out["tf32"][4:]):
-        assert float((a - b).abs().max()) < 2e-2
-    assert float((out["fp32"][3] - out["tf32"][3]).abs().max()) < 1e-3      # log-prob of a = mu + sigma*eps does not depend on mu
-    assert torch.isfinite(out["tf32"][0]).all() and torch.isfinite(out["tf32"][1]).all()
+    tol = CHAIN_TOL[precision]
+    errs = [float((a - b).abs().max()) for a, b in zip(out["fp32"], out[precision])]
+    print(f"[{precision}, hist={hist}] max abs diff to the fp32 path: mean {errs[0]:.3g} value {errs[1]:.3g} action {errs[2]:.3g} log-prob {errs[3]:.3g} bootstrap {errs[4]:.3g}")
+    for i in (0, 1, 2, 4):
+        assert errs[i] < tol["fwd"], (i, errs[i])
+    assert errs[3] < 1e-3                                          # log-prob of a = mu + sigma*eps does not depend on mu
+    assert all(torch.isfinite(t).all() for t in out[precision])
 
 
-def test_fused_chain_backward_matches_fp32_path_many_tiles():
-    """Mini-batch gradient through the fused forward + backward chains and the MN-major weight-gradient GEMMs (TF32) against
-    the exact-fp32 layer-wise path of the same library, at a row count that gives every CTA several tiles plus a ragged one.
-    Stated tolerance: per parameter tensor ||g_tf32 - g_fp32|| <= 5e-2 ||g_fp32|| (+ 1e-7 abs), mean losses within 1 %."""
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+def test_fused_chain_backward_matches_fp32_path_many_tiles(precision):
+    """Mini-batch gradient through the fused forward chains (loss in the epilogue), backward chains and the MN-major weight-gradient GEMMs
+    against the exact-fp32 layer-wise path of the same library, at a row count that gives every CTA several tile pairs plus a ragged one.
+    Tolerances: CHAIN_TOL, per parameter tensor ||g - g_fp32|| <= tol ||g_fp32|| (+ 1e-7 abs)."""
     import ctypes as C
     from dwbc_b200 import _lib as L
     g = np.load(os.path.join(G, "ppo.npz"))
@@ -306,21 +338,26 @@ def test_fused_chain_backward_matches_fp32_path_many_tiles():
     s.actions_log_prob.normal_(generator=gen).sub_(20.0)
     idx = torch.randperm(N * T, device="cuda", generator=gen)
     ac = alg.actor_critic
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", precision):
         alg.precision = prec
-        alg._set_precision()
         h = alg._fill_hp()
         alg._losses.zero_()
         L.check(L.lib().dwbc_ppo_minibatch_grad(C.addressof(ac.net_cfg), L.ptr(ac.flat), s.c_struct_ptr(), L.ptr(idx), N * T, C.addressof(h),
                                                 L.ptr(alg.grad), L.ptr(alg._losses), L.ptr(alg._workspace(N * T)), L.stream_ptr()), "grad")
         grads[prec] = {k: v.clone() for k, v in ac.unflat(alg.grad).items()}
         losses[prec] = alg._losses.clone()
+    tol = CHAIN_TOL[precision]
+    worst = ("", 0.0)
     for k in grads["fp32"]:
-        a, b = grads["fp32"][k].double(), grads["tf32"][k].double()
+        a, b = grads["fp32"][k].double(), grads[precision][k].double()
         assert torch.isfinite(b).all(), k
-        assert float((a - b).norm()) <= 5e-2 * float(a.norm()) + 1e-7, (k, float((a - b).norm()), float(a.norm()))
-    for i in range(3):
-        assert abs(float(losses["tf32"][i] - losses["fp32"][i])) <= 1e-2 * abs(float(losses["fp32"][i])) + 1e-5
+        rel = float((a - b).norm()) / max(float(a.norm()), 1e-12)
+        if float(a.norm()) > 1e-6 and rel > worst[1]:
+            worst = (k, rel)
+        assert float((a - b).norm()) <= tol["grad"] * float(a.norm()) + 1e-7, (k, float((a - b).norm()), float(a.norm()))
+    lerr = max(abs(float(losses[precision][i] - losses["fp32"][i])) / (abs(float(losses["fp32"][i])) + 1e-3) for i in range(4))
+    print(f"[{precision}] worst ||dg||/||g|| = {worst[1]:.3g} ({worst[0]}), losses rel {lerr:.3g}")
+    assert lerr <= tol["loss"]
 
 
 def test_dagger_update_tf32_path_within_stated_tolerance():
