@@ -99,6 +99,8 @@ class WidowGo1Params:
     num_priv: int = 24
     history_len: int = 10
     action_hist_len: int = 4            # action_delay + 2 (WG:541, WGC:120)
+    action_delay: int = 2               # WGC:120; the policy action applied is action_history_buf[:, -action_delay - 1] (WG:1167-1168)
+    clip_actions: float = 100.0         # WGC:116 normalization.clip_actions (WG:1163)
     feet_indices: List[int] = field(default_factory=lambda: [5, 9, 13, 17])   # FL,FR,RL,RR foot
     penalized_contact_indices: List[int] = field(default_factory=lambda: [1, 3, 7, 11, 15])
     termination_contact_indices: List[int] = field(default_factory=list)     # WGC:179 -> empty
@@ -290,7 +292,8 @@ class WidowGo1Params:
             num_envs=num_envs, num_dofs=len(dof_names), num_actions=cfg.env.num_actions,
             num_bodies=num_bodies, gripper_idx=gripper_idx, num_prop=cfg.env.num_proprio,
             num_priv=cfg.env.num_priv, history_len=cfg.env.history_len,
-            action_hist_len=cfg.env.action_delay + 2, feet_indices=list(feet_indices),
+            action_hist_len=cfg.env.action_delay + 2, action_delay=cfg.env.action_delay, clip_actions=cfg.normalization.clip_actions,
+            feet_indices=list(feet_indices),
             penalized_contact_indices=list(penalized_contact_indices),
             termination_contact_indices=list(termination_contact_indices),
             dof_names=list(dof_names), reorder_dofs=cfg.env.reorder_dofs, dt=dt,

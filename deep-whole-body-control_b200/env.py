@@ -242,6 +242,8 @@ class FusedWidowGo1Core:
             self._derived_state[:, 27] = 0.0          # DWBC_DS_OOB_AGE: unknown history -> kernel takes the clipping path for H steps
         if "actions" not in st and "action_history_buf" in st:
             self.actions.copy_(self.action_history_buf[:, 1])      # [:, -action_delay-1] with AH = delay+2 (WG:541,1167)
+        if getattr(self, "_bound", False):
+            self._bind()                                           # height_samples is a NEW tensor: refresh the kernel's pointer table
 
     def bind_sim(self, **tensors):
         """Re-bind Isaac-Gym-owned buffers to external tensors (zero-copy gymtorch views):
@@ -260,6 +262,7 @@ class FusedWidowGo1Core:
         self._buf.obs_stride = self.obs_buf.stride(0)
 
     def _bind(self):
+        self._bound = True
         b, P = self._buf, L.ptr
         b.root_states, b.dof_state = P(self._root_states), P(self.dof_state)
         b.rigid_body_state, b.contact_forces = P(self._rigid_body_state), P(self._contact_forces)
@@ -301,10 +304,12 @@ class FusedWidowGo1Core:
     def pre_physics_step(self, policy_actions: torch.Tensor) -> torch.Tensor:
         """WG:1162-1173: permute raisim->IG, clip, FIFO push, delayed action -> self.actions."""
         p = self.p
-        L.check(self._lib.dwbc_pre_physics_actions(L.ptr(policy_actions.contiguous()), L.ptr(self._raisim2ig), 100.0,
+        if p.action_delay < 0 or p.action_hist_len != p.action_delay + 2:
+            raise L.DwbcError("action_delay = -1 (no delay FIFO, WG:1166) / a history length other than action_delay + 2 is not implemented")
+        delay_row = p.action_hist_len - p.action_delay - 1              # action_history_buf[:, -action_delay - 1] after the shift (WG:1167-1168)
+        L.check(self._lib.dwbc_pre_physics_actions(L.ptr(policy_actions.contiguous(), torch.float32), L.ptr(self._raisim2ig), float(p.clip_actions),
                                                    L.ptr(self.action_history_buf), L.ptr(self.actions), p.num_envs, p.num_actions,
-                                                   p.action_hist_len, 1,
-                                                   L.stream_ptr()), "dwbc_pre_physics_actions")
+                                                   p.action_hist_len, delay_row, L.stream_ptr()), "dwbc_pre_physics_actions")
         return self.actions
 
     def compute_torques(self, actions: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -333,6 +338,8 @@ class FusedWidowGo1Core:
         a.rand_uniform = None if rand is None else L.ptr(rand)
         a.seed, a.step = self.seed, self.common_step_counter
         a.do_push = int(self.p.push_robots and (self.common_step_counter % self.p.push_interval == 0))
+        self._pushed = bool(a.do_push)
+        self.reset_count = None
         self._stats.zero_()
         L.check(self._lib.dwbc_post_physics_step(C.addressof(self._cfg), C.addressof(self._buf), C.addressof(a), L.stream_ptr()),
                 "dwbc_post_physics_step")
@@ -358,6 +365,16 @@ class FusedWidowGo1Core:
         e["coeff_ang_vel_yaw_upper_bound"], e["coeff_ang_vel_yaw_lower_bound"] = cur.ang_vel_yaw_ranges[1], cur.ang_vel_yaw_ranges[0]
         e["coeff_tracking_ang_vel_yaw_exp"] = cur.reward_scales.get("tracking_ang_vel_yaw_exp", 0.0)
         self.reset_count = int(cnt)
+
+    @property
+    def sim_state_dirty(self) -> bool:
+        """True when the last post_physics_step changed simulator-owned state (`_root_states` on push steps, WG:804-814; `_root_states`
+        and `dof_state` of reset envs, WG:757-828), i.e. when the caller owes Isaac Gym the `gym.set_*_tensor` calls the reference
+        issues at WG:787,813,827.  Without per-step statistics (`sync_stats=False`: no host read of the reset count) every step counts
+        as dirty -- writing back an unchanged tensor is harmless, skipping a changed one silently drops the push / reset."""
+        if getattr(self, "_pushed", False) or not self.sync_stats:
+            return True
+        return bool(self.reset_count)
 
     def step(self, actions: torch.Tensor, physics=None):
         """VecEnv.step (WG:1156-1199).  `physics(env)` stands for the decimated Isaac Gym loop

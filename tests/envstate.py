@@ -16,6 +16,8 @@ from dwbc_b200 import synth  # noqa: E402
 ENV_CONFIGS = {
     # default widowGo1 flat config (BASELINE.json configs[1] semantics)
     "flat": dict(),
+    # BASELINE.json configs[2]: flat reward set + 187-point height scan on the widowGo1 field (WG:253: 10000 x 600 int16) + terrain curriculum
+    "rough": dict(measure_heights=True, tot_rows=10000, tot_cols=600, terrain_curriculum=True),
     # every optional branch: extra reward terms on both channels, termination terms, contact
     # termination, positive-reward clip off, height scan on, terrain curriculum on (LR:421-441)
     "full": dict(

@@ -21,14 +21,6 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _data(seed=3):
-    g = torch.Generator().manual_seed(seed)
-    N = NL * WORLD
-    return dict(obs=torch.randn(T + 1, N, 860, generator=g), actions=torch.randn(T, N, 18, generator=g), values=torch.randn(T, N, 2, generator=g),
-                rewards=torch.randn(T, N, 2, generator=g), log_prob=torch.randn(T, N, 2, generator=g) - 20.0,
-                dones=(torch.rand(T, N, 1, generator=g) < 0.05).to(torch.uint8))
-
-
 def _make(n_envs, device, world, group):
     from dwbc_b200.actor_critic import FlatActorCritic
     from dwbc_b200.ppo import FusedPPO
@@ -36,53 +28,27 @@ def _make(n_envs, device, world, group):
     ac = FlatActorCritic(device=device, seed=0, init_std=[[0.8, 1.0, 1.0] * 4 + [1.0] * 6], num_priv=24, num_hist=10, num_prop=76)
     hp = ppo_hp()
     hp.update(num_learning_epochs=2, num_mini_batches=2)
-    alg = FusedPPO(ac, device=device, world_size=world, process_group=group, **hp)
+    alg = FusedPPO(ac, device=device, world_size=world, process_group=group, precision="tf32x3", **hp)
     alg.init_storage(n_envs, T, [860], [None], [18])
     alg.counter = 1500
     return alg
 
 
-def _fill(alg, d, lo, hi, device):
-    s = alg.storage
-    s._obs_all.copy_(d["obs"][:, lo:hi].to(device))
-    for k, src in (("actions", "actions"), ("values", "values"), ("rewards", "rewards"), ("actions_log_prob", "log_prob"), ("dones", "dones")):
-        getattr(s, k).copy_(d[src][:, lo:hi].to(device))
-    s.step = T
-
-
 def _worker(rank, port, out):
     import torch.distributed as dist
+    from dwbc_b200 import shard
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = f"cuda:{rank}"
     dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=torch.device(dev))
     try:
-        d = _data()
-        alg = _make(NL, dev, WORLD, None)
-        _fill(alg, d, rank * NL, (rank + 1) * NL, dev)
-        alg.compute_returns(d["obs"][T, rank * NL:(rank + 1) * NL].to(dev))
-        perm = torch.randperm(T * NL, generator=torch.Generator().manual_seed(11))          # same local permutation on both ranks
-        adv = alg.storage.advantages.clone()
-        alg.update(indices=perm.to(dev))
-        flat = alg.actor_critic.flat.clone()
-        gathered = [torch.empty_like(flat) for _ in range(WORLD)]
-        dist.all_gather(gathered, flat)
-        assert torch.equal(gathered[0], gathered[1]), "replicas diverged"
+        r = shard.union_batch_parity(lambda n, w, g: _make(n, dev, w, g), rank, WORLD, dev, NL, T, 2)
         if rank == 0:
-            # single-GPU run on the union batch: env order = rank-0 envs then rank-1 envs; mini-batch k = both ranks' mini-batch k
-            N = NL * WORLD
-            ref = _make(N, dev, 1, None)
-            _fill(ref, d, 0, N, dev)
-            ref.compute_returns(d["obs"][T].to(dev))
-            np.testing.assert_allclose(adv.cpu().numpy(), ref.storage.advantages[:, :NL].cpu().numpy(), rtol=0, atol=2e-6)
-            mbs = perm.numel() // 2
-            t_, e_ = perm // NL, perm % NL
-            union = torch.cat([torch.cat([t_[k * mbs:(k + 1) * mbs] * N + r * NL + e_[k * mbs:(k + 1) * mbs] for r in range(WORLD)]) for k in range(2)])
-            ref.update(indices=union.to(dev))
+            assert r["replicas_identical"], "replicas diverged"
+            assert r["advantage_max_abs_diff"] <= 2e-6, r
             # Adam divides by |g| + 1e-8: a reduction-order difference of 1e-9 in a near-zero gradient moves that parameter by up to ~lr,
             # so the criterion is: no entry off by more than lr = 2e-4, and all but 0.1 % of the entries within 5e-6
-            diff = (ref.actor_critic.flat - flat).abs()
-            assert float(diff.max()) < 2e-4 and float((diff > 5e-6).float().mean()) < 1e-3, (float(diff.max()), float((diff > 5e-6).float().mean()))
+            assert r["param_max_abs_diff"] < 2e-4 and r["param_frac_beyond_5e_6"] < 1e-3, r
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
