@@ -189,6 +189,8 @@ class Workload:
             else:
                 env.bind_sim(**self.pool[t])
             env.set_obs_target(alg.storage.obs_row(t + 1))
+            st_ = alg.storage          # rewards / dones of this transition go straight into the storage rows
+            env.set_transition_target(st_.values[t], st_.rewards[t], st_.dones[t], alg.gamma)
             env.pre_physics_step(actions)
             if time_k1:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,7 +319,10 @@ def run_ours(args):
     k1_ms = k1_queued()
 
     # ---- the halves of an iteration on their own (max over ranks): rollout, bootstrap + GAE, update() ----
-    roll_ms = cuda_ms(lambda: w.rollout(), 3, barrier, device, world)
+    def roll():
+        w.obs = w.rollout()
+        w.alg.storage.clear()
+    roll_ms = cuda_ms(roll, 3, barrier, device, world)
     gae_ms = cuda_ms(lambda: w.alg.compute_returns(w.obs), 3, barrier, device, world)
     upd_ms = cuda_ms(lambda: w.alg.update(), 3, barrier, device, world)
     dag = None

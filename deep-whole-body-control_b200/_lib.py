@@ -63,7 +63,8 @@ class EnvBuffers(C.Structure):
         "action_history", "mass_params", "friction", "motor_strength", "env_origins", "box_env_origins_delta_y",
         "goal_state", "derived_state", "episode_length", "obs_history", "episode_sums", "height_samples",
         "measured_heights", "heights_obs", "terrain_levels", "terrain_types", "terrain_origins", "obs_buf")] + \
-        [("obs_stride", i64)] + [(n, vp) for n in ("rew_buf", "arm_rew_buf", "reset_buf", "time_out_buf", "episode_stats")]
+        [("obs_stride", i64)] + [(n, vp) for n in ("rew_buf", "arm_rew_buf", "reset_buf", "time_out_buf", "episode_stats",
+                                                   "store_values", "store_rewards", "store_dones")] + [("store_gamma", f32), ("reserved_", i32)]
 
 
 class StepArgs(C.Structure):

@@ -564,6 +564,12 @@ env_step_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant__ 
     B.arm_rew_buf[e] = rew[1];
     B.reset_buf[e] = reset ? 1 : 0;
     B.time_out_buf[e] = time_out ? 1 : 0;
+    if (B.store_rewards) {          // PPO.process_env_step's reward path (PPO:130-134) + dones (RS:102), straight into the storage rows
+      const float to = time_out ? 1.0f : 0.0f;
+      B.store_rewards[2 * (size_t)e] = rew[0] + B.store_gamma * (B.store_values[2 * (size_t)e] * to);
+      B.store_rewards[2 * (size_t)e + 1] = rew[1] + B.store_gamma * (B.store_values[2 * (size_t)e + 1] * to);
+      if (B.store_dones) B.store_dones[e] = reset ? 1 : 0;
+    }
   }
   if (cfg.measure_heights && B.heights_obs) {  // LR:221-223
     const int npts = cfg.n_height_x * cfg.n_height_y;
@@ -627,7 +633,7 @@ extern "C" int dwbc_post_physics_step(const DwbcEnvCfg* cfg, const DwbcEnvBuffer
       !buf->torques || !buf->actions || !buf->action_history || !buf->mass_params || !buf->friction || !buf->motor_strength ||
       !buf->env_origins || !buf->box_env_origins_delta_y || !buf->goal_state || !buf->derived_state || !buf->episode_length ||
       !buf->obs_history || !buf->episode_sums || !buf->obs_buf || !buf->rew_buf || !buf->arm_rew_buf || !buf->reset_buf ||
-      !buf->time_out_buf || !buf->episode_stats)
+      !buf->time_out_buf || !buf->episode_stats || (buf->store_rewards && !buf->store_values))
     return DWBC_ERR_ARG;
   // v2 (32 envs per CTA, TMA bulk copies) whenever the shard is a multiple of 32 envs and every block is 16-B aligned
   if (cfg->num_envs % 32 == 0 && aligned16(buf->root_states) && aligned16(buf->dof_state) && aligned16(buf->force_sensor) &&

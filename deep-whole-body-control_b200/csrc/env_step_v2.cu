@@ -763,6 +763,13 @@ env_step_v2_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant
     B.arm_rew_buf[e0 + tid] = sm[Ly::o_out + 2 * tid + 1];
     B.reset_buf[e0 + tid] = (f & F_RESET) ? 1 : 0;
     B.time_out_buf[e0 + tid] = (f & F_TIMEOUT) ? 1 : 0;
+    if (B.store_rewards) {          // PPO.process_env_step's reward path (PPO:130-134) + dones (RS:102), straight into the storage rows
+      const size_t e = (size_t)(e0 + tid);
+      const float to = (f & F_TIMEOUT) ? 1.0f : 0.0f;
+      B.store_rewards[2 * e] = sm[Ly::o_out + 2 * tid] + B.store_gamma * (B.store_values[2 * e] * to);
+      B.store_rewards[2 * e + 1] = sm[Ly::o_out + 2 * tid + 1] + B.store_gamma * (B.store_values[2 * e + 1] * to);
+      if (B.store_dones) B.store_dones[e] = (f & F_RESET) ? 1 : 0;
+    }
   }
   if (cfg.measure_heights && B.heights_obs) {  // LR:221-223
     const int npts = cfg.n_height_x * cfg.n_height_y;

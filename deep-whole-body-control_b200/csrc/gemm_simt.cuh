@@ -19,16 +19,22 @@ enum { ACT_NONE = 0, ACT_ELU = 1, ACT_TANH = 2 };
 struct RowMat {
   const float* p;       // base (already offset to the first column)
   const int64_t* idx;   // optional gather index over groups
-  int rpg;              // rows per group (1 = plain)
+  int rpg;              // rows per group (1 = plain); 0 = "tile image" (below)
   int64_t stride_g;     // floats between groups
   int64_t ld;           // floats between sub-rows of a group
+  // rpg == 0: the matrix [rows x 128] is stored as the fused chain kernels keep it in shared memory, one 64 KB image per 128-row tile
+  // (mlp_chain2.cuh: element (r, k) of a tile at float ((r/8)*32 + k/4)*32 + (r%8)*4 + k%4), so that a tile leaves / enters the SM as
+  // ONE bulk copy.  row() then returns the address of column 0 of the row; 16-byte piece c of the row sits 32*c floats further on.
+  __device__ __forceinline__ bool image() const { return rpg == 0; }
   __device__ __forceinline__ const float* row(int64_t r) const {
+    if (rpg == 0) return p + (r >> 7) * 16384 + ((r & 127) >> 3) * 1024 + (r & 7) * 4;
     if (rpg == 1) return p + (idx ? idx[r] : r) * stride_g;
     int64_t g = r / rpg, s = r - g * rpg;
     return p + (idx ? idx[g] : g) * stride_g + s * ld;
   }
 };
 inline RowMat rowmat(const float* p, int64_t ld) { return RowMat{p, nullptr, 1, ld, ld}; }
+inline RowMat rowmat_image(const float* p) { return RowMat{p, nullptr, 0, 128, 128}; }
 inline RowMat rowmat_gather(const float* p, const int64_t* idx, int64_t stride) { return RowMat{p, idx, 1, stride, stride}; }
 inline RowMat rowmat_grouped(const float* p, const int64_t* idx, int rpg, int64_t stride_g, int64_t ld) {
   return RowMat{p, idx, rpg, stride_g, ld};

@@ -77,20 +77,28 @@ static int maxdim(const DwbcNetCfg& n) {
   return (int)align_up(m, 4);
 }
 
+// activations / pre-activation gradients of 128-wide layers are kept as tile images by the tensor-core path (RowMat::image):
+// whole 128-row tiles, so the buffer covers the rows rounded up to a tile
+static inline bool img_dim(int d) { return d == 128; }
+static inline int64_t act_floats(int64_t rows, int d) { return img_dim(d) ? align_up(rows, 128) * 128 : rows * align_up(d, 4); }
+static inline RowMat act_mat(const float* p, int d) { return img_dim(d) ? rowmat_image(p) : rowmat(p, d); }
+
 static Plan make_plan(const DwbcNetCfg& n, int64_t rows, void* ws) {
   Plan p{};
   Bump b{reinterpret_cast<char*>(ws), 0};
+  p.queue = reinterpret_cast<int*>(b.f(64));      // FIRST: the same address whatever `rows` is (callers share one workspace between row counts;
+                                                  // the counters must stay zero between launches, nothing else may ever be laid over them)
   p.latent = last(n.priv_dims, n.n_priv_layers);
   p.maxw = maxdim(n);
   p.mean_ld = (int)align_up(n.n_leg + n.n_arm, 4);
   for (int i = 0; i < n.n_priv_layers; ++i) p.priv[i] = b.f(rows * align_up(n.priv_dims[i], 4));
-  for (int i = 0; i < n.n_actor_layers; ++i) p.ab[i] = b.f(rows * n.actor_dims[i]);
-  for (int i = 0; i < n.n_leg_layers; ++i) p.al[i] = b.f(rows * n.leg_dims[i]);
-  for (int i = 0; i < n.n_arm_layers; ++i) p.aa[i] = b.f(rows * n.arm_dims[i]);
+  for (int i = 0; i < n.n_actor_layers; ++i) p.ab[i] = b.f(act_floats(rows, n.actor_dims[i]));
+  for (int i = 0; i < n.n_leg_layers; ++i) p.al[i] = b.f(act_floats(rows, n.leg_dims[i]));
+  for (int i = 0; i < n.n_arm_layers; ++i) p.aa[i] = b.f(act_floats(rows, n.arm_dims[i]));
   p.mean = b.f(rows * p.mean_ld);
-  for (int i = 0; i < n.n_critic_layers; ++i) p.cb[i] = b.f(rows * n.critic_dims[i]);
-  for (int i = 0; i < n.n_leg_layers; ++i) p.cl[i] = b.f(rows * n.leg_dims[i]);
-  for (int i = 0; i < n.n_arm_layers; ++i) p.ca[i] = b.f(rows * n.arm_dims[i]);
+  for (int i = 0; i < n.n_critic_layers; ++i) p.cb[i] = b.f(act_floats(rows, n.critic_dims[i]));
+  for (int i = 0; i < n.n_leg_layers; ++i) p.cl[i] = b.f(act_floats(rows, n.leg_dims[i]));
+  for (int i = 0; i < n.n_arm_layers; ++i) p.ca[i] = b.f(act_floats(rows, n.arm_dims[i]));
   p.value = b.f(rows * 2);
   p.hproj = b.f(rows * n.num_hist * 32);
   p.hc1 = b.f(rows * 4 * 20);
@@ -98,13 +106,12 @@ static Plan make_plan(const DwbcNetCfg& n, int64_t rows, void* ws) {
   p.zh = b.f(rows * align_up(p.latent, 4));
   p.hw1 = b.f(20 * 128); p.hw2 = b.f(10 * 40); p.hwl = b.f(32 * 36);
   p.wpack = b.f(C2_PACK_FLOATS);
-  p.queue = reinterpret_cast<int*>(b.f(64));
   p.g_leg = b.f(rows * align_up(n.n_leg, 4)); p.g_arm = b.f(rows * align_up(n.n_arm, 4));
   p.g_vl = b.f(rows * 4); p.g_va = p.g_vl ? p.g_vl + 1 : nullptr; p.g_z = b.f(rows * align_up(p.latent, 4));
-  for (int i = 0; i < n.n_leg_layers; ++i) { p.dza_l[i] = b.f(rows * n.leg_dims[i]); p.dzc_l[i] = b.f(rows * n.leg_dims[i]); }
-  for (int i = 0; i < n.n_arm_layers; ++i) { p.dza_a[i] = b.f(rows * n.arm_dims[i]); p.dzc_a[i] = b.f(rows * n.arm_dims[i]); }
-  for (int i = 0; i < n.n_actor_layers; ++i) p.dza_b[i] = b.f(rows * n.actor_dims[i]);
-  for (int i = 0; i < n.n_critic_layers; ++i) p.dzc_b[i] = b.f(rows * n.critic_dims[i]);
+  for (int i = 0; i < n.n_leg_layers; ++i) { p.dza_l[i] = b.f(act_floats(rows, n.leg_dims[i])); p.dzc_l[i] = b.f(act_floats(rows, n.leg_dims[i])); }
+  for (int i = 0; i < n.n_arm_layers; ++i) { p.dza_a[i] = b.f(act_floats(rows, n.arm_dims[i])); p.dzc_a[i] = b.f(act_floats(rows, n.arm_dims[i])); }
+  for (int i = 0; i < n.n_actor_layers; ++i) p.dza_b[i] = b.f(act_floats(rows, n.actor_dims[i]));
+  for (int i = 0; i < n.n_critic_layers; ++i) p.dzc_b[i] = b.f(act_floats(rows, n.critic_dims[i]));
   for (int i = 0; i < n.n_priv_layers; ++i) p.dzp[i] = b.f(rows * align_up(n.priv_dims[i], 4));
   p.d0 = b.f(rows * p.maxw); p.d1 = b.f(rows * p.maxw); p.d2 = b.f(rows * p.maxw);
   p.dz = b.f(rows * align_up(p.latent, 4));
@@ -294,6 +301,7 @@ static bool chain_usable(const DwbcNetCfg& n, const Plan& p, const float* obs, i
   if (n.n_priv_layers != 2 || n.num_priv > 32 || n.priv_dims[0] > 64 || p.latent > 32) return false;
   if ((n.num_prop & 3) || (n.num_priv & 3) || (p.latent & 3) || C2_COL_PROP + n.num_prop > 128 || n.num_prop + n.num_priv > 128) return false;
   if ((obs_stride & 3) || !c2_aligned(obs)) return false;
+  if (n.n_leg > C2_GRP || n.n_arm > C2_GRP) return false;      // the epilogue hooks keep one action group in registers
   if (2 + n.n_actor_layers + n.n_leg_layers + n.n_arm_layers + 2 > C2_MAX_OPS) return false;
   if (n.n_critic_layers + n.n_leg_layers + n.n_arm_layers + 2 > C2_MAX_OPS) return false;
   return true;
@@ -302,9 +310,10 @@ static bool chain_usable(const DwbcNetCfg& n, const Plan& p, const float* obs, i
 // one head: optional trunk reload (the second head of a program), hidden layers in place, narrow last layer with its epilogue hook
 static void chain_head(C2Builder& b, const float* P, const float* trunk, int trunk_ld, bool reload, int in, int nl, const int32_t* dims, int n_out,
                        const int64_t* ow, const int64_t* ob, float* const* acts, bool store, float* out, int64_t ldo, int last_act, int fin, int fin_c) {
-  if (reload) b.load(rowmat(trunk, trunk_ld), in, 0, pad8(in), b.pr.n_ops);
+  if (reload) b.load(act_mat(trunk, trunk_ld), in, 0, pad8(in), b.pr.n_ops);
   for (int l = 0; l < nl; ++l) {
-    b.fwd(P + ow[l], in, P + ob[l], dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0, store ? acts[l] : nullptr, dims[l]);
+    b.fwd(P + ow[l], in, P + ob[l], dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0, store ? acts[l] : nullptr, dims[l],
+          FIN_NONE, 0, store && img_dim(dims[l]));
     in = dims[l];
   }
   b.fwd(P + ow[nl], in, P + ob[nl], n_out, last_act, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, -1, out, ldo, fin, fin_c);
@@ -333,11 +342,11 @@ static int build_forward(const DwbcNetCfg& n, const float* P, const float* obs, 
     // backbone layer 0 over cat([obs_prop, z]) (AC:211): z occupies tile columns [0, latent), obs_prop [32, 32 + num_prop)
     const int na = n.n_actor_layers;
     A->fwd(P + n.off_actor_w[0], in0, P + n.off_actor_b[0], n.actor_dims[0], ACT_ELU, 0, k0, 2, C2PackSeg{0, n.num_prop, p.latent},
-           C2PackSeg{C2_COL_PROP, 0, n.num_prop}, 0, (store || na == 1) ? p.ab[0] : nullptr, n.actor_dims[0]);
+           C2PackSeg{C2_COL_PROP, 0, n.num_prop}, 0, (store || na == 1) ? p.ab[0] : nullptr, n.actor_dims[0], FIN_NONE, 0, img_dim(n.actor_dims[0]) && (store || na == 1));
     int in = n.actor_dims[0];
     for (int l = 1; l < na; ++l) {                                                   // AC:211-213
       A->fwd(P + n.off_actor_w[l], in, P + n.off_actor_b[l], n.actor_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
-             (store || l == na - 1) ? p.ab[l] : nullptr, n.actor_dims[l]);
+             (store || l == na - 1) ? p.ab[l] : nullptr, n.actor_dims[l], FIN_NONE, 0, img_dim(n.actor_dims[l]) && (store || l == na - 1));
       in = n.actor_dims[l];
     }
     const int fin = fin_mode == 2 ? FIN_PPO : (fin_mode == 1 ? FIN_ACT : FIN_NONE);
@@ -354,7 +363,7 @@ static int build_forward(const DwbcNetCfg& n, const float* P, const float* obs, 
     const int nc = n.n_critic_layers;
     for (int l = 0; l < nc; ++l) {                                                   // AC:280-286
       C->fwd(P + n.off_critic_w[l], in, P + n.off_critic_b[l], n.critic_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
-             (store || l == nc - 1) ? p.cb[l] : nullptr, n.critic_dims[l]);
+             (store || l == nc - 1) ? p.cb[l] : nullptr, n.critic_dims[l], FIN_NONE, 0, img_dim(n.critic_dims[l]) && (store || l == nc - 1));
       in = n.critic_dims[l];
     }
     const int fin = fin_mode == 2 ? FIN_VALUE : FIN_NONE;
@@ -578,20 +587,20 @@ static void chain_head_bwd(C2Builder& b, const float* P, const HeadDesc& hd, con
     const int kpad = narrow ? pad8(g_ld) : pad8(out);
     const C2PackSeg seg{narrow ? g_col : 0, 0, out};
     if (l > 0)
-      b.bwd(P + hd.ow[l], in, in, 0, kpad, seg, ACT_ELU, hd.acts[l - 1], in, nullptr, 0, 0, hd.dz[l - 1], in);
+      b.bwd(P + hd.ow[l], in, in, 0, kpad, seg, ACT_ELU, hd.acts[l - 1], in, nullptr, 0, 0, hd.dz[l - 1], in, img_dim(in), img_dim(in));
     else if (!second)
       b.bwd(P + hd.ow[0], in, in, 0, kpad, seg, ACT_NONE, nullptr, 0, nullptr, 0, -1, scratch, trunk_dim);
     else
-      b.bwd(P + hd.ow[0], in, in, 0, kpad, seg, ACT_ELU, trunk, trunk_dim, scratch, trunk_dim, 0, dz_trunk, trunk_dim);
+      b.bwd(P + hd.ow[0], in, in, 0, kpad, seg, ACT_ELU, trunk, trunk_dim, scratch, trunk_dim, 0, dz_trunk, trunk_dim, img_dim(trunk_dim), img_dim(trunk_dim));
   }
 }
 
 static void head_wgrad(WGroupBuilder& wb, float* grad, const HeadDesc& hd, RowMat trunk, int trunk_dim) {
   for (int l = hd.nl; l >= 0; --l) {
     const int in = l == 0 ? trunk_dim : hd.dims[l - 1];
-    RowMat G = l == hd.nl ? hd.g_out : rowmat(hd.dz[l], hd.dims[l]);
+    RowMat G = l == hd.nl ? hd.g_out : act_mat(hd.dz[l], hd.dims[l]);
     const int gout = l == hd.nl ? hd.n_out : hd.dims[l];
-    RowMat X = l == 0 ? trunk : rowmat(hd.acts[l - 1], hd.dims[l - 1]);
+    RowMat X = l == 0 ? trunk : act_mat(hd.acts[l - 1], hd.dims[l - 1]);
     wb.add(G, X, grad + hd.ow[l], in, grad + hd.ob[l], gout, in);
   }
 }
@@ -617,7 +626,7 @@ static int build_backward(const DwbcNetCfg& n, const float* P, const Plan& p, C2
   chain_head_bwd(C, P, d.ca, p.g_vl, 4, 1, ctd, p.cb[cnb - 1], true, p.d1, p.dzc_b[cnb - 1]);
   for (int l = cnb - 1; l >= 1; --l)
     C.bwd(P + n.off_critic_w[l], n.critic_dims[l - 1], n.critic_dims[l - 1], 0, pad8(n.critic_dims[l]), C2PackSeg{0, 0, n.critic_dims[l]}, ACT_ELU,
-          p.cb[l - 1], n.critic_dims[l - 1], nullptr, 0, l - 1 > 0 ? 0 : -1, p.dzc_b[l - 1], n.critic_dims[l - 1]);
+          p.cb[l - 1], n.critic_dims[l - 1], nullptr, 0, 0, p.dzc_b[l - 1], n.critic_dims[l - 1], img_dim(n.critic_dims[l - 1]), img_dim(n.critic_dims[l - 1]));
   C.finish();
   // ---- actor + privileged encoder ----
   const int anb = n.n_actor_layers, atd = n.actor_dims[anb - 1];
@@ -625,7 +634,7 @@ static int build_backward(const DwbcNetCfg& n, const float* P, const Plan& p, C2
   chain_head_bwd(A, P, d.aa, p.g_arm, garm_ld, 0, atd, p.ab[anb - 1], true, p.d0, p.dza_b[anb - 1]);
   for (int l = anb - 1; l >= 1; --l)
     A.bwd(P + n.off_actor_w[l], n.actor_dims[l - 1], n.actor_dims[l - 1], 0, pad8(n.actor_dims[l]), C2PackSeg{0, 0, n.actor_dims[l]}, ACT_ELU,
-          p.ab[l - 1], n.actor_dims[l - 1], nullptr, 0, 0, p.dza_b[l - 1], n.actor_dims[l - 1]);
+          p.ab[l - 1], n.actor_dims[l - 1], nullptr, 0, 0, p.dza_b[l - 1], n.actor_dims[l - 1], img_dim(n.actor_dims[l - 1]), img_dim(n.actor_dims[l - 1]));
   const int in0 = n.num_prop + p.latent, np = n.n_priv_layers;
   float* z = p.priv[np - 1];
   // dL/dz = policy path through the latent columns of backbone layer 0 + privileged-latent regulariser (g_z), through the encoder's last ELU
@@ -651,19 +660,19 @@ static int weight_gradients(const DwbcNetCfg& n, float* grad, const DwbcStorage*
   float* z = p.priv[np - 1];
   RowMat obs_all = rowmat_gather(s->observations, idx, s->obs_stride);
   WGroupBuilder wb;
-  head_wgrad(wb, grad, d.cl, rowmat(p.cb[cnb - 1], ctd), ctd);
-  head_wgrad(wb, grad, d.ca, rowmat(p.cb[cnb - 1], ctd), ctd);
+  head_wgrad(wb, grad, d.cl, act_mat(p.cb[cnb - 1], ctd), ctd);
+  head_wgrad(wb, grad, d.ca, act_mat(p.cb[cnb - 1], ctd), ctd);
   for (int l = cnb - 1; l >= 0; --l) {
     const int in = l == 0 ? n.num_prop + n.num_priv : n.critic_dims[l - 1];
-    wb.add(rowmat(p.dzc_b[l], n.critic_dims[l]), l == 0 ? obs_all : rowmat(p.cb[l - 1], in), grad + n.off_critic_w[l], in, grad + n.off_critic_b[l],
+    wb.add(act_mat(p.dzc_b[l], n.critic_dims[l]), l == 0 ? obs_all : act_mat(p.cb[l - 1], in), grad + n.off_critic_w[l], in, grad + n.off_critic_b[l],
            n.critic_dims[l], in);
   }
-  head_wgrad(wb, grad, d.al, rowmat(p.ab[anb - 1], atd), atd);
-  head_wgrad(wb, grad, d.aa, rowmat(p.ab[anb - 1], atd), atd);
+  head_wgrad(wb, grad, d.al, act_mat(p.ab[anb - 1], atd), atd);
+  head_wgrad(wb, grad, d.aa, act_mat(p.ab[anb - 1], atd), atd);
   for (int l = anb - 1; l >= 1; --l)
-    wb.add(rowmat(p.dza_b[l], n.actor_dims[l]), rowmat(p.ab[l - 1], n.actor_dims[l - 1]), grad + n.off_actor_w[l], n.actor_dims[l - 1],
+    wb.add(act_mat(p.dza_b[l], n.actor_dims[l]), act_mat(p.ab[l - 1], n.actor_dims[l - 1]), grad + n.off_actor_w[l], n.actor_dims[l - 1],
            grad + n.off_actor_b[l], n.actor_dims[l], n.actor_dims[l - 1]);
-  RowMat G0 = rowmat(p.dza_b[0], n.actor_dims[0]);
+  RowMat G0 = act_mat(p.dza_b[0], n.actor_dims[0]);
   wb.add(G0, obs_all, grad + n.off_actor_w[0], in0, grad + n.off_actor_b[0], n.actor_dims[0], n.num_prop);
   wb.add(G0, rowmat(z, Lld), grad + n.off_actor_w[0] + n.num_prop, in0, nullptr, n.actor_dims[0], p.latent);
   for (int l = np - 1; l >= 0; --l) {

@@ -22,13 +22,19 @@
 // (8-row x 16-byte core matrices, LBO = 128 B, SBO = 4096 B).  TMEM: slot s owns columns [256 s, 256 s + 256):
 // accumulator D at +0 (lane = row, column = output feature), A_lo at +128 (lane = row, column = k).
 #pragma once
+#include <stdlib.h>
+
 #include "gemm_tc2.cuh"
 
 namespace dwbc {
 
 constexpr int C2_MAX_OPS = 12, C2_MAX_LOADS = 6, C2_MAX_PACK = 36;   // pack items of one launch: forward + backward programs of both networks
 constexpr int C2_TILE = 128 * 128;                       // floats per operand tile
-constexpr int C2_WORKERS = 16;                           // epilogue / load warps: lane quarter = warp % 4, column group = warp / 4
+constexpr int C2_WORKERS = 8;                            // epilogue / load warps: lane quarter = warp % 4, column group = warp / 4
+constexpr int C2_H = C2_WORKERS / 4;                     // column groups: a warp takes the 32-column chunks ci with ci % C2_H == its group
+constexpr int C2_CPW = 4 / C2_H;                         // chunks per warp and op (N <= 128).  Eight warps (+ the MMA warp) leave 224 registers per
+                                                         // thread: two chunks of accumulator, activation and low-part values stay in registers (with
+                                                         // sixteen warps the 96-register cap spilled ~1 KB per thread and the epilogue ran from local memory)
 constexpr int C2_THREADS = 32 * (C2_WORKERS + 1);        // + the MMA warp (warp 16)
 constexpr int C2_NW = 32 * C2_WORKERS;                   // 512 worker threads
 constexpr int C2_SMEM_FLOATS = 3 * C2_TILE + 2 * 128;    // tile X, tile Y, weight image, two bias slots
@@ -41,6 +47,7 @@ struct C2Load {
   int col0;          // destination column (multiple of 4)
   int zero_to;       // columns [col0 + ncols, zero_to) are zero-filled (K padding of the consuming op)
   int before_op;     // issued once the ops < before_op of the slot have retired (0: with the item)
+  int img;           // 1: src.p is a tile-image buffer (RowMat::image): the whole 128 x 128 tile arrives as ONE bulk copy (ncols = 128, col0 = 0)
 };
 struct C2Op {
   const float* wp;       // packed image: canonical K-major [npad x kpad] weights, then [npad] bias
@@ -56,12 +63,15 @@ struct C2Op {
   const float* xact; int64_t ldx;     // backward: activation OUTPUT [M x ldx] whose derivative multiplies; null: none
   const float* add; int64_t ldadd;    // backward: optional addend [M x ldadd]
   int fin, fin_c;        // epilogue hook of a head's last op and its channel (0 leg, 1 arm)
+  int y_img;             // 1: y is a tile-image buffer: the MMA warp sends the finished tile there with one bulk copy (no thread stores)
+  int x_img;             // 1: xact is a tile-image buffer
 };
-struct C2Prog {
-  int M, n_loads, n_ops;
+struct alignas(16) C2Prog {
+  int M, n_loads, n_ops, pad_;
   C2Load ld[C2_MAX_LOADS];
   C2Op op[C2_MAX_OPS];
 };
+static_assert(sizeof(C2Prog) % 16 == 0, "copied to shared memory in 16-byte pieces");
 
 // everything the epilogue hooks need (AC:326-345, PPO:166-221)
 struct FinArgs {
@@ -128,7 +138,7 @@ __global__ void pack_weights2_kernel(const __grid_constant__ C2PackList pl) {
 
 // ---- device helpers ---------------------------------------------------------------------------------------------------
 struct C2Shared {
-  uint64_t w_full, w_free, ready[2], mma_done[2];
+  uint64_t w_full, w_free, ready[2], mma_done[2], ld_bar;
   uint32_t tmem_base;
   int item;
 };
@@ -141,6 +151,13 @@ __device__ __forceinline__ void c2_bulk_g2s(void* dst_smem, const void* src, uin
                "r"(bytes), "r"(tc_smem_u32(bar))
                : "memory");
 }
+// shared -> global bulk copy of this thread's bulk group (the tile images of the activations)
+__device__ __forceinline__ void c2_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tc_smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void c2_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be overwritten
+__device__ __forceinline__ void c2_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes complete
 // tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column per k)
 __device__ __forceinline__ void c2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -162,8 +179,24 @@ __device__ __forceinline__ void c2_st32(uint32_t taddr, const float* v) {
       "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// elect.sync: true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool c2_elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void c2_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void c2_wbar() { asm volatile("bar.sync 1, %0;" ::"n"(C2_NW) : "memory"); }     // the sixteen worker warps
+// hand-over of a worker warp: all its lanes have written (and fenced), ONE lane arrives (512 single-thread arrivals on one mbarrier
+// serialise to ~2 k cycles per op; 16 do not)
+__device__ __forceinline__ void c2_warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) t2_arrive(bar);
+}
 
 constexpr float C2_LOG_SQRT_2PI = 0.91893853320467274178f;
 
@@ -179,47 +212,82 @@ __device__ __forceinline__ void c2_bias_act(float* v, const float* bias, int nva
 }
 
 // ---- epilogue hooks: one thread per row, v[0 .. N) = the head's outputs of that row ---------------------------------------
+// Both action-group hooks first pull everything they need into registers with independent (8-byte vector) loads, then compute, then
+// store: written element by element the compiler had to order every load after the previous store (possible aliasing), i.e. a dozen
+// dependent global round trips per row.  A group has at most 16 actions (host check), rows of the [.., n_act] tensors are 8-byte aligned
+// at both group offsets when n_act and n_leg are even (host check; else the scalar path).
+constexpr int C2_GRP = 16;
+__device__ __forceinline__ void c2_ld_group(const float* p, int cnt, bool vec2, float* out) {
+  if (vec2) {
+#pragma unroll
+    for (int i = 0; i < C2_GRP; i += 2)
+      if (i < cnt) { const float2 t = *reinterpret_cast<const float2*>(p + i); out[i] = t.x; out[i + 1] = t.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C2_GRP; ++i)
+      if (i < cnt) out[i] = p[i];
+  }
+}
+__device__ __forceinline__ void c2_st_group(float* p, int cnt, bool vec2, const float* v) {
+  if (vec2) {
+#pragma unroll
+    for (int i = 0; i < C2_GRP; i += 2)
+      if (i < cnt) *reinterpret_cast<float2*>(p + i) = make_float2(v[i], v[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < C2_GRP; ++i)
+      if (i < cnt) p[i] = v[i];
+  }
+}
 // FIN_ACT (PPO:119-123, AC:326-345): group c = 0 legs (columns [0, n_leg)), 1 arm ([n_leg, n_act))
 __device__ __forceinline__ void c2_fin_act(const FinArgs& f, int c, int64_t m, bool on, const float* v) {
   if (!on) return;
   const int off = c == 0 ? 0 : f.n_leg, cnt = c == 0 ? f.n_leg : f.n_act - f.n_leg;
+  const bool vec2 = ((f.n_act | f.n_leg) & 1) == 0;
+  float sg[C2_GRP], ep[C2_GRP], ac[C2_GRP], mu[C2_GRP];
+  c2_ld_group(f.std + off, cnt, vec2, sg);
+  c2_ld_group(f.eps + m * f.n_act + off, cnt, vec2, ep);
   float lp = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {            // compile-time indices keep v[] in registers
+  for (int i = 0; i < C2_GRP; ++i) {            // compile-time indices keep the arrays in registers
     if (i < cnt) {
-      const float mu = v[i], sg = f.std[off + i];
-      const float a = mu + sg * f.eps[m * f.n_act + off + i];
-      const float d = a - mu;
-      lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
-      f.actions[m * f.n_act + off + i] = a;
-      f.mean_out[m * f.n_act + off + i] = mu;
-      f.sigma_out[m * f.n_act + off + i] = sg;
+      mu[i] = v[i];
+      ac[i] = mu[i] + sg[i] * ep[i];
+      const float d = ac[i] - mu[i];
+      lp += -(d * d) / (2.0f * (sg[i] * sg[i])) - logf(sg[i]) - C2_LOG_SQRT_2PI;
     }
   }
+  c2_st_group(f.actions + m * f.n_act + off, cnt, vec2, ac);
+  c2_st_group(f.mean_out + m * f.n_act + off, cnt, vec2, mu);
+  c2_st_group(f.sigma_out + m * f.n_act + off, cnt, vec2, sg);
   f.log_prob[2 * m + c] = lp;
 }
 // FIN_PPO (AC:341-345, PPO:199-205): log-prob of the stored action, ratio, mixed advantage, clipped surrogate, entropy and
 // the gradients w.r.t. the mean (through the tanh, AC:157,170) and std of this group
 __device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, bool on, const float* v, int lane) {
   const int off = c == 0 ? 0 : f.n_leg, cnt = c == 0 ? f.n_leg : f.n_act - f.n_leg;
+  const bool vec2 = ((f.n_act | f.n_leg) & 1) == 0;
   const float inv2m = 1.0f / (2.0f * (float)f.rows);
   float l_surr = 0.0f, l_ent = 0.0f, glp = 0.0f;
-  int64_t src = 0;
+  float sg[C2_GRP], act[C2_GRP], gm[C2_GRP];
+  c2_ld_group(f.std + off, cnt, vec2, sg);
   if (on) {
-    src = f.idx ? f.idx[m] : m;
-    const float* act = f.s_actions + src * f.n_act + off;
+    const int64_t src = f.idx ? f.idx[m] : m;
+    c2_ld_group(f.s_actions + src * f.n_act + off, cnt, vec2, act);
+    const float2 adv = *reinterpret_cast<const float2*>(f.adv + 2 * src);
+    const float old_lp = f.old_logp[2 * src + c];
     float lp = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < C2_GRP; ++i) {
       if (i < cnt) {
-        const float sg = f.std[off + i], d = act[i] - v[i];
-        lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - C2_LOG_SQRT_2PI;
-        l_ent += 0.5f + C2_LOG_SQRT_2PI + logf(sg);
+        const float d = act[i] - v[i];
+        const float ls = logf(sg[i]);
+        lp += -(d * d) / (2.0f * (sg[i] * sg[i])) - ls - C2_LOG_SQRT_2PI;
+        l_ent += 0.5f + C2_LOG_SQRT_2PI + ls;
       }
     }
-    const float a0 = f.adv[2 * src], a1 = f.adv[2 * src + 1];
-    const float mix = c == 0 ? a0 + f.rho * a1 : a1 + f.rho * a0;                   // PPO:199-201
-    const float ratio = expf(lp - f.old_logp[2 * src + c]);                          // PPO:202
+    const float mix = c == 0 ? adv.x + f.rho * adv.y : adv.y + f.rho * adv.x;      // PPO:199-201
+    const float ratio = expf(lp - old_lp);                                           // PPO:202
     const float rc = fminf(fmaxf(ratio, 1.0f - f.clip), 1.0f + f.clip);
     const float s1 = -mix * ratio, s2 = -mix * rc;                                   // PPO:203-205
     l_surr = fmaxf(s1, s2);
@@ -229,34 +297,40 @@ __device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, b
     else if (s1 == s2) g = 0.5f * -mix + (inside ? 0.5f * -mix : 0.0f);
     else g = inside ? -mix : 0.0f;
     glp = inv2m * g * ratio;
-    float* grow = c == 0 ? f.g_leg + m * f.gleg_ld : f.g_arm + m * f.garm_ld;
     const int gld = c == 0 ? f.gleg_ld : f.garm_ld;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < gld) {
-        float gm = 0.0f;
-        if (i < cnt) {
-          const float sg = f.std[off + i], d = act[i] - v[i];
-          gm = glp * d / (sg * sg) * (1.0f - v[i] * v[i]);
-        }
-        grow[i] = gm;
+    for (int i = 0; i < C2_GRP; ++i) {
+      gm[i] = 0.0f;
+      if (i < cnt) {
+        const float d = act[i] - v[i];
+        gm[i] = glp * d / (sg[i] * sg[i]) * (1.0f - v[i] * v[i]);
       }
+    }
+    float* grow = c == 0 ? f.g_leg + m * f.gleg_ld : f.g_arm + m * f.garm_ld;
+    if ((gld & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < C2_GRP; i += 4)
+        if (i < gld) *reinterpret_cast<float4*>(grow + i) = make_float4(gm[i], gm[i + 1], gm[i + 2], gm[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < C2_GRP; ++i)
+        if (i < gld) grow[i] = gm[i];
     }
   }
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {               // gradient of std: one atomic per warp and column
+  for (int i = 0; i < C2_GRP; ++i) {           // gradient of std: one atomic per warp and column
     if (i < cnt) {                             // (warp-uniform)
       float gs = 0.0f;
       if (on) {
-        const float sg = f.std[off + i], d = f.s_actions[src * f.n_act + off + i] - v[i];
-        gs = glp * ((d * d) / (sg * sg * sg) - 1.0f / sg) - f.c_ent * inv2m / sg;
+        const float d = act[i] - v[i];
+        gs = glp * ((d * d) / (sg[i] * sg[i] * sg[i]) - 1.0f / sg[i]) - f.c_ent * inv2m / sg[i];
       }
       gs = warp_sum(gs);
       if (lane == 0) atomicAdd(f.grad_std + off + i, gs);
     }
   }
   const float ss = warp_sum(l_surr * inv2m), se = warp_sum(l_ent * inv2m);
-  if (lane == 0) { atomicAdd(f.losses + 0, ss); atomicAdd(f.losses + 3, se); }
+  if (lane == 0) { atomicAdd(f.losses + 0, ss); atomicAdd(f.losses + 1 + 2, se); }
 }
 // FIN_VALUE (PPO:209-216), channel c
 __device__ __forceinline__ void c2_fin_value(const FinArgs& f, int c, int64_t m, bool on, float val, int lane) {
@@ -309,6 +383,8 @@ __device__ __forceinline__ void c2_fin_reg(const FinArgs& f, int64_t m, bool on,
 __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_constant__ C2Launch L, const int tiles) {
   extern __shared__ __align__(1024) float c2_smem[];
   __shared__ C2Shared sh;
+  __shared__ __align__(16) C2Prog sprog;
+  int cur_prog = -1;
   float* tile[2] = {c2_smem, c2_smem + C2_TILE};
   float* wbuf = c2_smem + 2 * C2_TILE;
   float* bias_s = c2_smem + 3 * C2_TILE;                 // two slots of 128 (parity of the CTA-wide op counter)
@@ -316,7 +392,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
   if (tid == 0) {
     tc_mbar_init(&sh.w_full, 1);
     tc_mbar_init(&sh.w_free, 1);
-    for (int s = 0; s < 2; ++s) { tc_mbar_init(&sh.ready[s], C2_NW); tc_mbar_init(&sh.mma_done[s], 1); }
+    tc_mbar_init(&sh.ld_bar, 1);
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&sh.ready[s], C2_WORKERS); tc_mbar_init(&sh.mma_done[s], 1); }   // one arrival per worker WARP
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == C2_WORKERS) tc_tmem_alloc(&sh.tmem_base, 512);
@@ -330,8 +407,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
 
   // running counters, identical in every thread: ops of all items so far (bias slot parity) and ops per slot (phase of that
   // slot's ready / mma_done barriers: a slot without a tile in some item does not advance)
-  uint32_t nop = 0, cnt[2] = {0, 0};
+  uint32_t nop = 0, cnt[2] = {0, 0}, rcnt[2] = {0, 0}, nld = 0;   // rcnt: phases of ready[] (one per op + one after the last op of an item); nld: ld_bar
   uint32_t nw = 0, nf = 0;          // weight images fetched (phase of w_full) / released (phase of w_free): used by the MMA thread only
+  if (tid == 0) T2_STAMP(62);       // profiling aid (tools/chain_profile.py): clock64 stamps of the CTA's FIRST item, 6 per op
 
   for (;;) {
     // ---- next work item ----
@@ -341,72 +419,124 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
     const int item = sh.item;
     if (item >= items) break;
     const int pi = item / pairs;                         // program 0 (the longer one) first
-    const C2Prog& pr = L.p[pi];
+    // the item's program goes to shared memory: read through the kernel parameter, every field access with a run-time op index is an
+    // indexed constant-bank load (LDC c[0x0][R + off]) -- a long-scoreboard stall in front of most addresses and predicates of the epilogue
+    if (pi != cur_prog) {
+      const int4* src = reinterpret_cast<const int4*>(&L.p[pi]);
+      int4* dst = reinterpret_cast<int4*>(&sprog);
+      for (int k = tid; k < (int)(sizeof(C2Prog) / 16); k += C2_THREADS) dst[k] = src[k];
+      cur_prog = pi;
+      __syncthreads();
+    }
+    const C2Prog& pr = sprog;
     const int t0 = (item - pi * pairs) * L.pair;
     const int nslots = min(L.pair, tiles - t0);
     const int nops = pr.n_ops;
 
     if (warp == C2_WORKERS) {
-      // ===================== weight copies + MMA issue (one thread) =====================
-      if (lane == 0) {
-        const uint32_t b0 = tc_smem_u32(wbuf);
-        auto fetch = [&](const float* img, uint32_t wbytes, uint32_t bbytes, uint32_t slot) {
+      // ===================== weight copies + MMA issue =====================
+      // The WHOLE warp runs this control flow (converged, every value warp-uniform); only the instructions that must be issued once sit
+      // under elect.sync.  Issued from inside `if (lane == 0)` the compiler could not prove the descriptors uniform and wrapped every
+      // tcgen05.mma in an elect / 7 x R2UR.BROADCAST / branch loop: ~300 cycles per MMA, i.e. the MMA thread, not the tensor core or the
+      // epilogue, set the pace of the whole kernel.
+      const uint32_t b0 = tc_smem_u32(wbuf);
+      auto fetch = [&](const float* img, uint32_t wbytes, uint32_t bbytes, uint32_t slot) {
+        if (c2_elect()) {
           c2_expect_tx(&sh.w_full, wbytes + bbytes);
           c2_bulk_g2s(wbuf, img, wbytes, &sh.w_full);
           if (bbytes) c2_bulk_g2s(bias_s + slot * 128, img + (wbytes >> 2), bbytes, &sh.w_full);
-        };
-        uint32_t n = nop;
-        {
-          const C2Op& o0 = pr.op[0];
-          fetch(o0.wp, (uint32_t)(o0.npad * o0.kpad) * 4u, (uint32_t)o0.npad * 4u, n & 1);
         }
-        for (int i = 0; i < nops; ++i, ++n) {
-          const C2Op& o = pr.op[i];
-          const uint32_t idesc = tc_idesc(o.npad, false, false);
-          const uint32_t wsbo = (uint32_t)(o.kpad >> 2) * 128u;
+        __syncwarp();
+      };
+      uint32_t n = nop;
+      {
+        const C2Op& o0 = pr.op[0];
+        fetch(o0.wp, (uint32_t)(o0.npad * o0.kpad) * 4u, (uint32_t)o0.npad * 4u, n & 1);
+      }
+      for (int i = 0; i < nops; ++i, ++n) {
+        const C2Op& o = pr.op[i];
+        const uint32_t idesc = tc_idesc(o.npad, false, false);
+        const uint32_t wsbo = (uint32_t)(o.kpad >> 2) * 128u;
+        const int nk = o.kpad >> 3;
+        tc_mbar_wait(&sh.w_full, nw & 1); ++nw;
+        if (lane == 0 && nop == 0 && i < 10) T2_STAMP(6 * i + 0);
+        // the previous op left a finished tile behind: if its output is a tile image it goes out now, as one 64 KB bulk copy issued right
+        // before the MMAs that read the same tile; its shared-memory reads must have completed before the epilogue of THIS op may overwrite
+        // the tile, i.e. before mma_done is signalled
+        const bool st_prev = i > 0 && pr.op[i - 1].y_img != 0;
+        bool reload_next = false;                      // an image written earlier is re-read before the next op: those writes must have landed
+        for (int l = 0; l < pr.n_loads; ++l) reload_next |= pr.ld[l].before_op == i + 1 && pr.ld[l].img != 0;
+        for (int s = 0; s < nslots; ++s) {
+          tc_mbar_wait(&sh.ready[s], (rcnt[s] + i) & 1);   // loads landed / previous epilogue done: operand tile written, accumulator drained
+          if (lane == 0 && nop == 0 && i < 10) T2_STAMP(6 * i + 1 + s);
+          tc_fence_async_smem();                       // generic-proxy tile writes -> async-proxy MMA / bulk-copy reads
+          tc_fence_after();
+          const uint32_t a0 = tc_smem_u32(tile[s]) + (uint32_t)(o.a_col0 >> 2) * 128u;
+          const uint32_t dt = tmem + s * 256;
+          if (c2_elect()) {
+            if (st_prev) c2_bulk_s2g(pr.op[i - 1].y + (size_t)(t0 + s) * C2_TILE, tile[s], C2_TILE * 4);
+            // one K step (8 columns = two 16-byte pieces) advances both start addresses by 256 bytes: +16 in the descriptors' address field
+            uint64_t ad = tc_desc(a0, 128, 4096), bd = tc_desc(b0, 128, wsbo);
+            tc_mma_tf32(dt, ad, bd, idesc, 0u);
+#pragma unroll 4
+            for (int k = 1; k < nk; ++k) { ad += 16; bd += 16; tc_mma_tf32(dt, ad, bd, idesc, 1u); }
+            if (x3) {
+              bd = tc_desc(b0, 128, wsbo);
+              uint32_t at = dt + 128 + o.a_col0;
+#pragma unroll 4
+              for (int k = 0; k < nk; ++k, at += 8, bd += 16) c2_mma_ts(dt, at, bd, idesc, 1u);
+            } else {
+              if (reload_next) c2_bulk_wait_all(); else if (st_prev) c2_bulk_wait_read();
+              tc_commit(&sh.mma_done[s]);
+            }
+          }
+          __syncwarp();
+        }
+        if (c2_elect()) tc_commit(&sh.w_free);
+        __syncwarp();
+        tc_mbar_wait(&sh.w_free, nf & 1); ++nf;        // every MMA reading the image has retired: the buffer may be refilled
+        if (lane == 0 && nop == 0 && i < 10) T2_STAMP(6 * i + 3);
+        if (x3) {
+          fetch(o.wp_lo, (uint32_t)(o.npad * o.kpad) * 4u, 0u, 0);
           tc_mbar_wait(&sh.w_full, nw & 1); ++nw;
           for (int s = 0; s < nslots; ++s) {
-            tc_mbar_wait(&sh.ready[s], (cnt[s] + i) & 1);   // loads landed / previous epilogue done: operand tile written, accumulator drained
-            tc_fence_async_smem();                       // generic-proxy tile writes -> async-proxy MMA reads
-            tc_fence_after();
             const uint32_t a0 = tc_smem_u32(tile[s]) + (uint32_t)(o.a_col0 >> 2) * 128u;
             const uint32_t dt = tmem + s * 256;
-            for (int kk = 0; kk < o.kpad; kk += 8)
-              tc_mma_tf32(dt, tc_desc(a0 + (kk >> 2) * 128, 128, 4096), tc_desc(b0 + (kk >> 2) * 128, 128, wsbo), idesc, kk > 0 ? 1u : 0u);
-            if (x3) {
-              for (int kk = 0; kk < o.kpad; kk += 8)
-                c2_mma_ts(dt, dt + 128 + o.a_col0 + kk, tc_desc(b0 + (kk >> 2) * 128, 128, wsbo), idesc, 1u);
-            } else {
+            if (c2_elect()) {
+              uint64_t ad = tc_desc(a0, 128, 4096), bd = tc_desc(b0, 128, wsbo);
+#pragma unroll 4
+              for (int k = 0; k < nk; ++k, ad += 16, bd += 16) tc_mma_tf32(dt, ad, bd, idesc, 1u);
+              if (reload_next) c2_bulk_wait_all(); else if (st_prev) c2_bulk_wait_read();
               tc_commit(&sh.mma_done[s]);
             }
+            __syncwarp();
           }
-          tc_commit(&sh.w_free);
-          tc_mbar_wait(&sh.w_free, nf & 1); ++nf;        // every MMA reading the image has retired: the buffer may be refilled
-          if (x3) {
-            fetch(o.wp_lo, (uint32_t)(o.npad * o.kpad) * 4u, 0u, 0);
-            tc_mbar_wait(&sh.w_full, nw & 1); ++nw;
-            for (int s = 0; s < nslots; ++s) {
-              const uint32_t a0 = tc_smem_u32(tile[s]) + (uint32_t)(o.a_col0 >> 2) * 128u;
-              const uint32_t dt = tmem + s * 256;
-              for (int kk = 0; kk < o.kpad; kk += 8)
-                tc_mma_tf32(dt, tc_desc(a0 + (kk >> 2) * 128, 128, 4096), tc_desc(b0 + (kk >> 2) * 128, 128, wsbo), idesc, 1u);
-              tc_commit(&sh.mma_done[s]);
-            }
-            tc_commit(&sh.w_free);
-            tc_mbar_wait(&sh.w_free, nf & 1); ++nf;
-          }
-          if (i + 1 < nops) {
-            const C2Op& o1 = pr.op[i + 1];
-            fetch(o1.wp, (uint32_t)(o1.npad * o1.kpad) * 4u, (uint32_t)o1.npad * 4u, (n + 1) & 1);
-          }
+          if (c2_elect()) tc_commit(&sh.w_free);
+          __syncwarp();
+          tc_mbar_wait(&sh.w_free, nf & 1); ++nf;
+        }
+        if (i + 1 < nops) {
+          const C2Op& o1 = pr.op[i + 1];
+          fetch(o1.wp, (uint32_t)(o1.npad * o1.kpad) * 4u, (uint32_t)o1.npad * 4u, (n + 1) & 1);
         }
       }
-      __syncwarp();
+      // the last op's tiles: every slot is handed back once more; an image output leaves now, and the tiles may be reloaded (next item)
+      // only after the copies have read them
+      for (int s = 0; s < nslots; ++s) {
+        tc_mbar_wait(&sh.ready[s], (rcnt[s] + nops) & 1);
+        tc_fence_async_smem();
+        if (c2_elect()) {
+          if (pr.op[nops - 1].y_img) c2_bulk_s2g(pr.op[nops - 1].y + (size_t)(t0 + s) * C2_TILE, tile[s], C2_TILE * 4);
+          if (s + 1 == nslots) c2_bulk_wait_read();
+        }
+        __syncwarp();
+      }
     } else {
       // ===================== loads + epilogues (sixteen warps) =====================
       const int q = warp & 3, h = warp >> 2;               // TMEM lane quarter, column group (32-column chunks ci with ci % 4 == h)
       const int r = q * 32 + lane;                         // tile row of this thread in the epilogue
-      const int lrow = warp * 8 + (lane & 7), lpc = lane >> 3;   // load role: fixed row, 16-byte pieces lpc, lpc + 4, ...
+      constexpr int LRW = 128 / C2_WORKERS, LPS = 32 / LRW;     // load role: rows per warp, piece stride
+      const int lrow = warp * LRW + (lane % LRW), lpc = lane / LRW;   // fixed row, 16-byte pieces lpc, lpc + LPS, ...
 
       // cp.async of one load into the tile of slot s (no waiting); rows beyond the matrix are zero-filled
       auto issue_load = [&](const C2Load& ld, int s, int64_t m0, int rows) {
@@ -414,18 +544,18 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         const int c40 = ld.col0 >> 2, cpr = ld.ncols >> 2;
         const int z0 = (ld.col0 + ld.ncols) >> 2, z1 = ld.zero_to >> 2;
         float* rowbase = tl + ((size_t)(lrow >> 3) * 32) * 32 + (lrow & 7) * 4;
-        for (int cz = z0 + lpc; cz < z1; cz += 4) *reinterpret_cast<float4*>(rowbase + (size_t)cz * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int cz = z0 + lpc; cz < z1; cz += LPS) *reinterpret_cast<float4*>(rowbase + (size_t)cz * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool on = lrow < rows;
         const float* src = on ? ld.src.row(m0 + lrow) : ld.src.p;
         const uint32_t d0 = tc_smem_u32(rowbase);
-        for (int cc = lpc; cc < cpr; cc += 4)
+        for (int cc = lpc; cc < cpr; cc += LPS)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + (uint32_t)(c40 + cc) * 128u), "l"(src + 4 * cc), "r"(on ? 16 : 0)
                        : "memory");
       };
       // 3xTF32: low parts of tile columns [c_lo, c_hi) (whole 32-column chunks) -> A_lo of slot s
       auto split_cols = [&](int s, int c_lo, int c_hi) {
         const float* trow = tile[s] + ((size_t)(r >> 3) * 32) * 32 + (r & 7) * 4;
-        for (int ci = (c_lo >> 5) + h; ci * 32 < c_hi; ci += 4) {
+        for (int ci = (c_lo >> 5) + h; ci * 32 < c_hi; ci += C2_H) {
           float v[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -442,11 +572,24 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         for (int l = 0; l < pr.n_loads; ++l) any |= pr.ld[l].before_op == before;
         if (!any) return false;
         if (sync_first) c2_wbar();                       // every worker has finished writing / copying the tiles the loads overwrite
+        int nimg = 0;
         for (int s = 0; s < nslots; ++s) {
           const int64_t m0 = (int64_t)(t0 + s) * TC_M;
           const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
-          for (int l = 0; l < pr.n_loads; ++l)
-            if (pr.ld[l].before_op == before) issue_load(pr.ld[l], s, m0, rows);
+          for (int l = 0; l < pr.n_loads; ++l) {
+            if (pr.ld[l].before_op != before) continue;
+            if (pr.ld[l].img) ++nimg; else issue_load(pr.ld[l], s, m0, rows);
+          }
+        }
+        if (nimg) {                                      // tile images come back as one bulk copy each (warp-uniform count)
+          if (tid == 0) {
+            c2_expect_tx(&sh.ld_bar, (uint32_t)nimg * C2_TILE * 4u);
+            for (int s = 0; s < nslots; ++s)
+              for (int l = 0; l < pr.n_loads; ++l)
+                if (pr.ld[l].before_op == before && pr.ld[l].img) c2_bulk_g2s(tile[s], pr.ld[l].src.p + (size_t)(t0 + s) * C2_TILE, C2_TILE * 4, &sh.ld_bar);
+          }
+          tc_mbar_wait(&sh.ld_bar, nld & 1);
+          ++nld;
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         if (x3) {
@@ -463,32 +606,43 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
       do_loads(0, false);
       tc_fence_before();
       tc_fence_async_smem();
-      for (int s = 0; s < nslots; ++s) t2_arrive(&sh.ready[s]);
+      for (int s = 0; s < nslots; ++s) c2_warp_arrive(&sh.ready[s], lane);
 
       for (int i = 0; i < nops; ++i, ++n) {
         const C2Op& o = pr.op[i];
-        const int c0 = 32 * h;                             // this warp's chunk (every op has at most four chunks)
-        const bool mine = c0 < o.npad;
+        bool pending = false;                              // loads that precede op i+1 cover both slots and follow the last slot's epilogue
+        for (int l = 0; l < pr.n_loads; ++l) pending |= pr.ld[l].before_op == i + 1;
         for (int s = 0; s < nslots; ++s) {
           const int64_t m0 = (int64_t)(t0 + s) * TC_M;
           const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
           const bool on = r < rows;
-          // backward: the activation chunk whose derivative multiplies, fetched while the MMAs run
-          float x[32];
-          const bool use_x = o.mode == 1 && o.xact != nullptr && mine;
+          // backward: the activation chunks whose derivative multiplies, fetched while the MMAs run
+          float x[C2_CPW][32];
+          const bool use_x = o.mode == 1 && o.xact != nullptr;
           if (use_x) {
-            const float* xr = o.xact + (m0 + r) * o.ldx + c0;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (on && c0 + 4 * j4 < o.N) t = *reinterpret_cast<const float4*>(xr + 4 * j4);
-              x[4 * j4] = t.x; x[4 * j4 + 1] = t.y; x[4 * j4 + 2] = t.z; x[4 * j4 + 3] = t.w;
+            for (int u = 0; u < C2_CPW; ++u) {
+              const int c0 = 32 * (h + u * C2_H);
+              // row-major: 32 consecutive floats of the row; tile image: eight 16-byte pieces 128 bytes apart (eight rows share each line)
+              const float* xr = o.x_img ? o.xact + (size_t)(t0 + s) * C2_TILE + ((size_t)((r >> 3) * 32 + (c0 >> 2)) * 8 + (r & 7)) * 4
+                                        : o.xact + (m0 + r) * o.ldx + c0;
+              const int xst = o.x_img ? 32 : 4;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (on && c0 + 4 * j4 < o.N) t = *reinterpret_cast<const float4*>(xr + xst * j4);
+                x[u][4 * j4] = t.x; x[u][4 * j4 + 1] = t.y; x[u][4 * j4 + 2] = t.z; x[u][4 * j4 + 3] = t.w;
+              }
             }
           }
           tc_mbar_wait(&sh.mma_done[s], (cnt[s] + i) & 1);
           tc_fence_after();
-          float v[32];
-          if (mine) {
+          if (tid == 0 && s == 0 && nop == 0 && i < 10) T2_STAMP(6 * i + 4);
+#pragma unroll
+          for (int u = 0; u < C2_CPW; ++u) {
+            const int c0 = 32 * (h + u * C2_H);            // this warp's u-th chunk
+            if (c0 >= o.npad) continue;
+            float v[32];
             tc_ld32(tmem + s * 256 + ((uint32_t)(q * 32) << 16) + c0, v);
             if (o.mode == 0) {
               const float* bias = bias_s + (n & 1) * 128 + c0;
@@ -509,7 +663,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
               if (use_x) {
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {
-                  const float d = o.act == ACT_TANH ? 1.0f - x[jj] * x[jj] : (x[jj] > 0.0f ? 1.0f : x[jj] + 1.0f);   // AC ELU / tanh derivatives from the outputs
+                  const float xx = x[u][jj];
+                  const float d = o.act == ACT_TANH ? 1.0f - xx * xx : (xx > 0.0f ? 1.0f : xx + 1.0f);   // AC ELU / tanh derivatives from the outputs
                   v[jj] *= d;
                 }
               }
@@ -521,21 +676,14 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4)
                 *reinterpret_cast<float4*>(otile + (size_t)j4 * 32) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-              if (x3) {
-                float lo[32];
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj) lo[jj] = tf32_lo(v[jj]);
-                c2_st32(tmem + s * 256 + 128 + ((uint32_t)(q * 32) << 16) + o.out_col0 + c0, lo);
-                c2_wait_st();
-              }
             }
-            if (o.fin != FIN_NONE && h == 0) {
+            if (o.fin != FIN_NONE && c0 == 0) {
               if (o.fin == FIN_ACT) c2_fin_act(L.fin, o.fin_c, m0 + r, on, v);
               else if (o.fin == FIN_PPO) c2_fin_ppo(L.fin, o.fin_c, m0 + r, on, v, lane);
               else if (o.fin == FIN_VALUE) c2_fin_value(L.fin, o.fin_c, m0 + r, on, v[0], lane);
               else c2_fin_reg(L.fin, m0 + r, on, v, lane);
             }
-            if (o.y != nullptr && !o.copy_after && on) {       // straight from the registers: 128 contiguous bytes per thread
+            if (o.y != nullptr && !o.copy_after && !o.y_img && on) {       // straight from the registers: 128 contiguous bytes per thread
               float* yr = o.y + (m0 + r) * o.ldy + c0;
               if ((o.ldy & 3) == 0 && (o.N & 3) == 0) {
 #pragma unroll
@@ -547,36 +695,44 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
                   if (c0 + jj < o.N) yr[jj] = v[jj];
               }
             }
-          }
-          tc_fence_before();                               // tcgen05.ld / st of this op precede the hand-over
-          if (i + 1 < nops) {
-            bool pending = false;                          // loads that precede op i+1 cover both slots and follow the last slot's epilogue
-            for (int l = 0; l < pr.n_loads; ++l) pending |= pr.ld[l].before_op == i + 1;
-            if (!pending) {
-              tc_fence_async_smem();
-              t2_arrive(&sh.ready[s]);
-            } else if (s + 1 == nslots) {
-              do_loads(i + 1, true);
-              tc_fence_before();
-              tc_fence_async_smem();
-              for (int s2 = 0; s2 < nslots; ++s2) t2_arrive(&sh.ready[s2]);
+            if (x3 && o.out_col0 >= 0) {                       // low parts last, in place: v is dead afterwards
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] = tf32_lo(v[jj]);
+              c2_st32(tmem + s * 256 + 128 + ((uint32_t)(q * 32) << 16) + o.out_col0 + c0, v);
             }
           }
-          if (mine && o.y != nullptr && o.copy_after) {
-            // global copy of the chunk this warp just wrote, out of the tile: 8 rows x 64 contiguous bytes per instruction
+          if (x3 && o.out_col0 >= 0) c2_wait_st();
+          tc_fence_before();                               // tcgen05.ld / st of this op precede the hand-over
+          if (!pending || i + 1 == nops) {              // (after the last op too: the MMA warp sends image outputs off and frees the tiles)
+            tc_fence_async_smem();
+            c2_warp_arrive(&sh.ready[s], lane);
+          } else if (s + 1 == nslots) {
+            do_loads(i + 1, true);
+            tc_fence_before();
+            tc_fence_async_smem();
+            for (int s2 = 0; s2 < nslots; ++s2) c2_warp_arrive(&sh.ready[s2], lane);
+          }
+          if (tid == 0 && s + 1 == nslots && nop == 0 && i < 10) T2_STAMP(6 * i + 5);
+          if (o.y != nullptr && o.copy_after && !o.y_img) {
+            // global copy of the chunks this warp just wrote, out of the tile: 8 rows x 64 contiguous bytes per instruction
             __syncwarp();
             const int r8 = lane & 7, pp = lane >> 3;
             const float* tl = tile[s];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int rr = q * 32 + g * 8 + r8;
-              if (rr >= rows) continue;
-              const float* trow = tl + ((size_t)((rr >> 3) * 32 + ((o.out_col0 + c0) >> 2)) * 8 + r8) * 4;
-              float* yr = o.y + (m0 + rr) * o.ldy + c0;
+            for (int u = 0; u < C2_CPW; ++u) {
+              const int c0 = 32 * (h + u * C2_H);
+              if (c0 >= o.N) continue;
 #pragma unroll
-              for (int p0 = 0; p0 < 8; p0 += 4) {
-                const int piece = p0 + pp;
-                if (c0 + 4 * piece < o.N) *reinterpret_cast<float4*>(yr + 4 * piece) = *reinterpret_cast<const float4*>(trow + (size_t)piece * 32);
+              for (int g = 0; g < 4; ++g) {
+                const int rr = q * 32 + g * 8 + r8;
+                if (rr >= rows) continue;
+                const float* trow = tl + ((size_t)((rr >> 3) * 32 + ((o.out_col0 + c0) >> 2)) * 8 + r8) * 4;
+                float* yr = o.y + (m0 + rr) * o.ldy + c0;
+#pragma unroll
+                for (int p0 = 0; p0 < 8; p0 += 4) {
+                  const int piece = p0 + pp;
+                  if (c0 + 4 * piece < o.N) *reinterpret_cast<float4*>(yr + 4 * piece) = *reinterpret_cast<const float4*>(trow + (size_t)piece * 32);
+                }
               }
             }
           }
@@ -584,10 +740,12 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
       }
     }
     nop += nops;
-    for (int s = 0; s < nslots; ++s) cnt[s] += nops;
+    for (int s = 0; s < nslots; ++s) { cnt[s] += nops; rcnt[s] += nops + 1; }
   }
+  if (warp == C2_WORKERS && c2_elect()) c2_bulk_wait_all();      // the image stores of this CTA have landed
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) T2_STAMP(63);
   if (warp == C2_WORKERS) tc_tmem_dealloc(tmem, 512);
   if (tid == 0) {                        // the last CTA re-arms the queue for the next launch
     __threadfence();
@@ -615,9 +773,14 @@ struct C2Builder {
   bool x3, ok = true;
   C2Builder(C2PackList* pl_, int64_t* off_, int M, bool x3_) : pl(pl_), off(off_), x3(x3_) { pr.M = M; }
   void load(RowMat src, int ncols, int col0, int zero_to, int before_op) {
+    if (src.rpg == 0) {                 // tile image: the whole tile, one bulk copy
+      if (pr.n_loads >= C2_MAX_LOADS || ncols != 128 || col0 != 0 || zero_to != 128 || !c2_aligned(src.p)) { ok = false; return; }
+      pr.ld[pr.n_loads++] = C2Load{src, ncols, col0, zero_to, before_op, 1};
+      return;
+    }
     if (pr.n_loads >= C2_MAX_LOADS || (ncols & 3) || (col0 & 3) || (zero_to & 3) || zero_to < col0 + ncols || zero_to > 128 || !c2_aligned(src.p) ||
         (src.stride_g & 3) || (src.ld & 3) || src.rpg != 1) { ok = false; return; }
-    pr.ld[pr.n_loads++] = C2Load{src, ncols, col0, zero_to, before_op};
+    pr.ld[pr.n_loads++] = C2Load{src, ncols, col0, zero_to, before_op, 0};
   }
   C2Op* push(const float* W, int64_t ldw, const float* bias, int N, int kpad, int transpose, int nseg, C2PackSeg s0, C2PackSeg s1) {
     const int npad = (N + 15) & ~15;
@@ -637,23 +800,28 @@ struct C2Builder {
     return &o;
   }
   // y = act(A[:, a_col0 : a_col0 + kpad] W'^T + b): W [N x ldw]; tile column a_col0 + seg.kdst + j multiplies W[:, seg.ksrc + j]
+  // y_img: y is a tile-image buffer (only for full-width outputs written at tile column 0)
   void fwd(const float* W, int64_t ldw, const float* bias, int N, int act, int a_col0, int kpad, int nseg, C2PackSeg s0, C2PackSeg s1, int out_col0,
-           float* y, int64_t ldy, int fin = FIN_NONE, int fin_c = 0) {
+           float* y, int64_t ldy, int fin = FIN_NONE, int fin_c = 0, bool y_img = false) {
+    if (y_img && (N != 128 || out_col0 != 0 || !y || !c2_aligned(y))) { ok = false; return; }
     if ((a_col0 & 3) || a_col0 + kpad > 128 || (out_col0 >= 0 && ((out_col0 & 31) || out_col0 + ((N + 31) & ~31) > 128)) || (fin != FIN_NONE && N > 32)) { ok = false; return; }
     C2Op* o = push(W, ldw, bias, N, kpad, 0, nseg, s0, s1);
     if (!o) return;
     o->y = y; o->ldy = ldy; o->a_col0 = a_col0; o->act = act; o->out_col0 = out_col0; o->mode = 0; o->fin = fin; o->fin_c = fin_c;
+    o->y_img = y_img ? 1 : 0;
   }
   // dX[:, :Nin] = (dZ[:, a_col0 : a_col0 + kpad] W' (+ add)) (*) act'(xact): W [Kout x ldw] (row = output feature);
   // tile column a_col0 + seg.kdst + j multiplies row seg.ksrc + j of W
   void bwd(const float* W, int64_t ldw, int Nin, int a_col0, int kpad, C2PackSeg seg, int act, const float* xact, int64_t ldx, const float* add,
-           int64_t ldadd, int out_col0, float* y, int64_t ldy) {
+           int64_t ldadd, int out_col0, float* y, int64_t ldy, bool x_img = false, bool y_img = false) {
+    if ((y_img && (Nin != 128 || out_col0 != 0 || !y)) || (x_img && Nin != 128)) { ok = false; return; }
     if ((a_col0 & 3) || a_col0 + kpad > 128 || (Nin & 3) || (xact && ((ldx & 3) || !c2_aligned(xact))) || (add && ((ldadd & 3) || !c2_aligned(add))) ||
         (out_col0 >= 0 && (out_col0 & 31))) { ok = false; return; }
     C2Op* o = push(W, ldw, nullptr, Nin, kpad, 1, 1, seg, C2PackSeg{0, 0, 0});
     if (!o) return;
     o->y = y; o->ldy = ldy; o->a_col0 = a_col0; o->act = act; o->out_col0 = out_col0; o->mode = 1;
     o->xact = act == ACT_NONE ? nullptr : xact; o->ldx = ldx; o->add = add; o->ldadd = ldadd;
+    o->x_img = x_img ? 1 : 0; o->y_img = y_img ? 1 : 0;
   }
   // global copies may be taken from the tile after the hand-over only if nothing overwrites those tile columns before the
   // same warp's next epilogue: same column mapping in the next op (out_col0 0 or none) and no load in between
@@ -663,8 +831,12 @@ struct C2Builder {
       bool load_next = false;
       for (int l = 0; l < pr.n_loads; ++l) load_next |= pr.ld[l].before_op == i + 1;
       const bool next_ok = i + 1 == pr.n_ops || pr.op[i + 1].out_col0 <= 0;
-      o.copy_after = (o.y && o.out_col0 == 0 && !load_next && next_ok && (o.ldy & 3) == 0 && (o.N & 3) == 0 && c2_aligned(o.y)) ? 1 : 0;
+      o.copy_after = (o.y && !o.y_img && o.out_col0 == 0 && !load_next && next_ok && (o.ldy & 3) == 0 && (o.N & 3) == 0 && c2_aligned(o.y)) ? 1 : 0;
       if (o.y && (o.ldy & 3) == 0 && (o.N & 3) == 0 && !c2_aligned(o.y)) ok = false;   // vector stores need 16-byte aligned rows
+      // an image written by op i is sent off while op i+1 runs and must have landed before it is re-read: not by a load in front of op i+1
+      if (o.y_img)
+        for (int l = 0; l < pr.n_loads; ++l)
+          if (pr.ld[l].img && pr.ld[l].src.p == o.y && pr.ld[l].before_op <= i + 1) ok = false;
     }
   }
 };
@@ -683,6 +855,11 @@ inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fi
     if (pr.M <= 0 || pr.M != L.p[0].M || pr.n_ops <= 0 || pr.n_ops > C2_MAX_OPS || pr.n_loads < 0 || pr.n_loads > C2_MAX_LOADS) return DWBC_ERR_ARG;
   }
   if (!queue) return DWBC_ERR_ARG;
+  if (const char* dbg = getenv("DWBC_C2_DEBUG")) {      // timing experiments only (results invalid): 1 = drop every global activation store
+    if (atoi(dbg) & 1)
+      for (int k = 0; k < L.nprog; ++k)
+        for (int i = 0; i < L.p[k].n_ops; ++i) L.p[k].op[i].y = nullptr;
+  }
   static int sms = 0;
   if (!sms) {
     int dev = 0;

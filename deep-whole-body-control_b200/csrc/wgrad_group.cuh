@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
       const float* base = op == 0 ? g.G.p : g.X.p;
       const int64_t* ro = sh.rowoff + 64 * op;
       const int ncol = op == 0 ? g.Mo : g.Ni;
+      const int pst = (op == 0 ? g.G : g.X).image() ? 32 : 4;
       if (op == 0 ? g.fastG : g.fastX) {
         const int cpr = ncol >> 2;                          // 16-byte pieces per row
         const uint32_t d0 = tc_smem_u32(dst);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
         const int sh2 = 31 - __clz(cpr);
         for (int i = pt; i < WCH * cpr; i += 256) {
           const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;          // row, piece
-          const float* src = k < nk ? base + ro[k] + 4 * c4 : base;
+          const float* src = k < nk ? base + ro[k] + pst * c4 : base;      // piece stride: 4 floats (row-major) or 32 (tile image)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + piece_off(k, c4)), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
         }
       } else {
@@ -243,6 +244,7 @@ struct WGroupBuilder {
     it.G = G; it.X = X; it.dW = dW; it.lddw = lddw; it.db = db; it.Mo = Mo; it.Ni = Ni;
     it.fastG = rowmat_vec_ok(G) && (Mo & 3) == 0;
     it.fastX = rowmat_vec_ok(X) && (Ni & 3) == 0;
+    if ((G.rpg == 0 && !it.fastG) || (X.rpg == 0 && !it.fastX)) ok = false;      // tile images are always read in 16-byte pieces
   }
 };
 

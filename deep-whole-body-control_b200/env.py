@@ -261,6 +261,22 @@ class FusedWidowGo1Core:
         self._buf.obs_buf = self.obs_buf.data_ptr()
         self._buf.obs_stride = self.obs_buf.stride(0)
 
+    def set_transition_target(self, values: Optional[torch.Tensor], rewards: Optional[torch.Tensor] = None, dones: Optional[torch.Tensor] = None,
+                              gamma: float = 0.0):
+        """Direct-to-storage transition: with `rewards` = row t of RolloutStorage.rewards [N,2] (and `values` = the values
+        PPO.act wrote for this step, `dones` = row t of RolloutStorage.dones, uint8) the post-physics kernel itself performs
+        PPO.process_env_step's reward path (PPO:130-134) and the dones store (RS:102); FusedPPO.process_env_step recognises the rows and
+        launches nothing.  `set_transition_target(None)` switches it off."""
+        b = self._buf
+        if values is None or rewards is None:
+            b.store_values = b.store_rewards = b.store_dones = None
+            self._stored_rows = None
+            return
+        b.store_values, b.store_rewards = L.ptr(values, torch.float32), L.ptr(rewards, torch.float32)
+        b.store_dones = None if dones is None else L.ptr(dones, torch.uint8)
+        b.store_gamma = float(gamma)
+        self._stored_rows = (rewards.data_ptr(), None if dones is None else dones.data_ptr())
+
     def _bind(self):
         self._bound = True
         b, P = self._buf, L.ptr
@@ -340,12 +356,22 @@ class FusedWidowGo1Core:
         a.do_push = int(self.p.push_robots and (self.common_step_counter % self.p.push_interval == 0))
         self._pushed = bool(a.do_push)
         self.reset_count = None
-        self._stats.zero_()
+        if self.sync_stats:
+            self._stats.zero_()        # per-step episode statistics (WG:743-750); without them the accumulators are read by episode_stats()
         L.check(self._lib.dwbc_post_physics_step(C.addressof(self._cfg), C.addressof(self._buf), C.addressof(a), L.stream_ptr()),
                 "dwbc_post_physics_step")
         self.extras["time_outs"] = self.time_out_buf
+        self.extras["dwbc_stored_rows"] = getattr(self, "_stored_rows", None)
         if self.sync_stats:
             self._fill_episode_extras()
+
+    def episode_stats(self, reset: bool = True):
+        """`extras['episode']` over every episode that ended since the last call (one D2H read; for sync_stats=False loops that log once per
+        iteration instead of syncing on every step like WG:705)."""
+        self._fill_episode_extras()
+        if reset:
+            self._stats.zero_()
+        return self.extras["episode"]
 
     def _fill_episode_extras(self):
         """extras['episode'] (WG:743-750).  One D2H read of the per-step stats block (the reference

@@ -78,6 +78,7 @@ class FusedPPO:
         self.world_size, self.process_group = world_size, process_group
         self._zh_all = None
         self._packed = False          # tensor-core weight images in the workspace match the current parameters (rollout reuse)
+        self._eps_all, self._eps_valid = None, False
         self.precision = precision
         ac = actor_critic
         self.optimizer = _AdamState(ac, 0, ac.num_params, learning_rate)                  # PPO:75
@@ -150,9 +151,21 @@ class FusedPPO:
         self._set_precision()
         n = obs.shape[0]
         if eps is None:
-            if self._eps is None or self._eps.shape[0] != n:
-                self._eps = torch.empty(n, ac.num_leg_actions + ac.num_arm_actions, device=self.device)
-            eps = self._eps.normal_(generator=self.generator)
+            na = ac.num_leg_actions + ac.num_arm_actions
+            if s is not None and n == s.num_envs and s.step < s.num_transitions_per_env:
+                # the standard normals of a whole rollout are drawn by ONE generator launch at its first step (Normal.sample() of AC:337-339
+                # draws the same distribution once per step)
+                if self._eps_all is None or self._eps_all.shape[:2] != (s.num_transitions_per_env, n):
+                    self._eps_all = torch.empty(s.num_transitions_per_env, n, na, device=self.device)
+                    self._eps_valid = False
+                if s.step == 0 or not self._eps_valid:
+                    self._eps_all.normal_(generator=self.generator)
+                    self._eps_valid = True
+                eps = self._eps_all[s.step]
+            else:
+                if self._eps is None or self._eps.shape[0] != n:
+                    self._eps = torch.empty(n, na, device=self.device)
+                eps = self._eps.normal_(generator=self.generator)
         if s is not None and s.step < s.num_transitions_per_env and n == s.num_envs:
             t = s.step
             if obs.data_ptr() != s.observations[t].data_ptr():
@@ -182,11 +195,15 @@ class FusedPPO:
         if s.step >= s.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")                               # RS:96-97
         t = s.step
-        to = infos.get("time_outs") if isinstance(infos, dict) else None
-        d8 = dones if dones.dtype in (torch.uint8, torch.bool) else (dones != 0)
-        L.check(self._lib.dwbc_store_rewards(L.ptr(rewards), L.ptr(arm_rewards), L.ptr(s.values[t]),
-                                             None if to is None else L.ptr(to.contiguous()), L.ptr(d8.contiguous()), self.gamma,
-                                             L.ptr(s.rewards[t]), L.ptr(s.dones[t]), s.num_envs, L.stream_ptr()), "dwbc_store_rewards")
+        stored = infos.get("dwbc_stored_rows") if isinstance(infos, dict) else None
+        if stored is None or stored != (s.rewards[t].data_ptr(), s.dones[t].data_ptr()):
+            # (else: the post-physics kernel already wrote this step's rewards / dones rows, FusedWidowGo1Core.set_transition_target)
+            to = infos.get("time_outs") if isinstance(infos, dict) else None
+            to8 = None if to is None else (to if to.dtype in (torch.uint8, torch.bool) else (to != 0)).contiguous()
+            d8 = (dones if dones.dtype in (torch.uint8, torch.bool) else (dones != 0)).contiguous()
+            L.check(self._lib.dwbc_store_rewards(L.ptr(rewards.float().contiguous(), torch.float32), L.ptr(arm_rewards.float().contiguous(), torch.float32),
+                                                 L.ptr(s.values[t]), L.ptr(to8, (torch.uint8, torch.bool)), L.ptr(d8, (torch.uint8, torch.bool)), self.gamma,
+                                                 L.ptr(s.rewards[t]), L.ptr(s.dones[t]), s.num_envs, L.stream_ptr()), "dwbc_store_rewards")
         s.step += 1
         self.transition.clear()
 

@@ -166,6 +166,14 @@ typedef struct DwbcEnvBuffers {
   uint8_t* time_out_buf;         /* [N] torch.bool */
   float* episode_stats;          /* [1+sums_stride]: #resets, then per-slot sum over reset envs (atomics;
                                     caller zeroes before the step; WG:743-750 means = sum/count/T_ep) */
+  /* optional direct-to-storage transition: with store_rewards != NULL the kernel also performs
+   * PPO.process_env_step's reward path (PPO:130-134) and the dones store (RS:102) of this step:
+   *   store_rewards[n,:] = (rew, arm_rew) + store_gamma * store_values[n,:] * time_out[n];  store_dones[n] = reset[n]  */
+  const float* store_values;     /* [N,2] values PPO.act produced for this step */
+  float* store_rewards;          /* [N,2] row of RolloutStorage.rewards */
+  uint8_t* store_dones;          /* [N]   row of RolloutStorage.dones (uint8, may be NULL) */
+  float store_gamma;
+  int32_t reserved_;
 } DwbcEnvBuffers;
 
 /* Per-step arguments: curriculum outputs (WG:678-692) and RNG source. */
@@ -267,7 +275,9 @@ typedef struct DwbcPdCfg {
 int dwbc_compute_torques(const DwbcPdCfg* cfg, const float* actions, const float* dof_state, const float* motor_strength,
                          float* torques, int32_t num_envs, dwbc_stream_t stream);
 
-/* Bytes of device workspace the forward / update entry points need for `rows` rows. */
+/* Bytes of device workspace the forward / update entry points need for `rows` rows.  The workspace must be ZERO-FILLED when it is
+ * first handed to the library (its first 256 bytes hold the work-queue counters of the fused chain kernel, which every launch leaves
+ * at zero again); one workspace sized for the largest `rows` may be shared by calls with smaller `rows`. */
 int64_t dwbc_workspace_bytes(const DwbcNetCfg* net, int64_t rows);
 
 /* PPO.act (PPO:115-127 = AC:337-353): obs[N,obs_stride] -> mean, sigma, actions = mean +

@@ -162,6 +162,39 @@ def test_obs_written_directly_into_storage_row_and_structure():
         assert float(obs.abs().max()) <= 100.0
 
 
+def test_transition_written_directly_into_storage_rows():
+    """with set_transition_target the post-physics kernel performs PPO.process_env_step's reward path (PPO:130-134) and the dones
+    store (RS:102) itself; bit-identical to the separate dwbc_store_rewards launch, and FusedPPO.process_env_step recognises the rows."""
+    from dwbc_b200.actor_critic import FlatActorCritic
+    from dwbc_b200.ppo import FusedPPO
+    seed, N, T = 13, 2048, 3
+    p = E.make_params("flat", N)
+    st = E.initial(p, seed)
+    a, b = make_core(p, st, seed=5), make_core(p, st, seed=5)
+    a.common_step_counter = b.common_step_counter = 148
+    algs = []
+    for _ in range(2):
+        alg = FusedPPO(FlatActorCritic(device="cuda:0", seed=0, num_priv=24, num_hist=10, num_prop=76), device="cuda:0", gamma=0.99)
+        alg.init_storage(N, T, [p.num_obs], [None], [p.num_actions])
+        alg.storage.values.normal_(generator=torch.Generator(device="cuda").manual_seed(3))
+        algs.append(alg)
+    for t in range(T):
+        sim = synth.sim_state(p, seed, t + 1)
+        load_sim(a, p, sim)
+        load_sim(b, p, sim)
+        sa, sb = algs[0].storage, algs[1].storage
+        b.set_transition_target(sb.values[t], sb.rewards[t], sb.dones[t], 0.99)
+        a.post_physics_step()
+        b.post_physics_step()
+        n0 = int(a._lib.dwbc_launch_count())
+        algs[0].process_env_step(a.rew_buf, a.arm_rew_buf, a.reset_buf, a.extras)
+        n1 = int(a._lib.dwbc_launch_count())
+        algs[1].process_env_step(b.rew_buf, b.arm_rew_buf, b.reset_buf, b.extras)
+        assert n1 - n0 == 1 and int(a._lib.dwbc_launch_count()) == n1          # the second call launched nothing
+        assert torch.equal(sa.rewards[t], sb.rewards[t]) and torch.equal(sa.dones[t], sb.dones[t])
+    assert float(algs[0].storage.rewards.abs().sum()) > 0 and int(a.time_out_buf.sum() + sa.dones.sum()) >= 0
+
+
 @pytest.mark.gpu
 def test_torque_controller_matches_reference_golden():
     """dwbc_compute_torques (WG:1262-1295) against the golden vectors of the unmodified reference: exact fp32 arithmetic (the kernel is

@@ -6,7 +6,7 @@ from dwbc_b200.actor_critic import FlatActorCritic
 from dwbc_b200.ppo import FusedPPO
 N, T = 4096, 40
 ac = FlatActorCritic(device="cuda:0", seed=0, init_std=[[0.8, 1.0, 1.0] * 4 + [1.0] * 6], num_priv=24, num_hist=10, num_prop=76)
-alg = FusedPPO(ac, device="cuda:0", precision="tf32", num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, learning_rate=2e-4,
+alg = FusedPPO(ac, device="cuda:0", precision=(sys.argv[1] if len(sys.argv) > 1 else "tf32"), num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, learning_rate=2e-4,
                mixing_schedule=[1.0, 0, 1], priv_reg_coef_schedual=[0, 1, 1000, 1000])
 alg.init_storage(N, T, [860], [None], [18]); alg.counter = 1500
 s = alg.storage
