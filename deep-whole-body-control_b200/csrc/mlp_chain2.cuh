@@ -189,6 +189,19 @@ __device__ __forceinline__ bool c2_elect() {
       : "=r"(pred));
   return pred != 0;
 }
+// tcgen05.ld of 32 lanes x 32 columns without the wait (tc_ld32 waits right away)
+__device__ __forceinline__ void c2_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void c2_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void c2_wbar() { asm volatile("bar.sync 1, %0;" ::"n"(C2_NW) : "memory"); }     // the sixteen worker warps
 // hand-over of a worker warp: all its lanes have written (and fenced), ONE lane arrives (512 single-thread arrivals on one mbarrier
@@ -200,14 +213,31 @@ __device__ __forceinline__ void c2_warp_arrive(uint64_t* bar, int lane) {
 
 constexpr float C2_LOG_SQRT_2PI = 0.91893853320467274178f;
 
-template <int kAct>
+template <int kAct, bool kFull>
 __device__ __forceinline__ void c2_bias_act(float* v, const float* bias, int nvalid) {
 #pragma unroll
-  for (int jj = 0; jj < 32; ++jj) {
-    float x = v[jj] + bias[jj];
-    if (kAct == ACT_ELU) x = x > 0.0f ? x : __expf(x) - 1.0f;
-    if (kAct == ACT_TANH) x = t2_tanh(x);
-    v[jj] = jj < nvalid ? x : 0.0f;
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * j4);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int jj = 4 * j4 + e;
+      float x = v[jj] + bb[e];
+      if (kAct == ACT_ELU) x = fmaxf(x, 0.0f) + (__expf(fminf(x, 0.0f)) - 1.0f);      // ELU without a select: max(x,0) + (e^{min(x,0)} - 1)
+      if (kAct == ACT_TANH) x = t2_tanh(x);
+      v[jj] = (kFull || jj < nvalid) ? x : 0.0f;
+    }
+  }
+}
+__device__ __forceinline__ void c2_bias_act_any(float* v, const float* bias, int act, int nvalid) {
+  if (nvalid >= 32) {
+    if (act == ACT_ELU) c2_bias_act<ACT_ELU, true>(v, bias, 32);
+    else if (act == ACT_TANH) c2_bias_act<ACT_TANH, true>(v, bias, 32);
+    else c2_bias_act<ACT_NONE, true>(v, bias, 32);
+  } else {
+    if (act == ACT_ELU) c2_bias_act<ACT_ELU, false>(v, bias, nvalid);
+    else if (act == ACT_TANH) c2_bias_act<ACT_TANH, false>(v, bias, nvalid);
+    else c2_bias_act<ACT_NONE, false>(v, bias, nvalid);
   }
 }
 
@@ -645,10 +675,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
             float v[32];
             tc_ld32(tmem + s * 256 + ((uint32_t)(q * 32) << 16) + c0, v);
             if (o.mode == 0) {
-              const float* bias = bias_s + (n & 1) * 128 + c0;
-              if (o.act == ACT_ELU) c2_bias_act<ACT_ELU>(v, bias, o.N - c0);
-              else if (o.act == ACT_TANH) c2_bias_act<ACT_TANH>(v, bias, o.N - c0);
-              else c2_bias_act<ACT_NONE>(v, bias, o.N - c0);
+              c2_bias_act_any(v, bias_s + (n & 1) * 128 + c0, o.act, o.N - c0);
             } else {
               if (o.add != nullptr && on) {
                 const float* ar = o.add + (m0 + r) * o.ldadd + c0;

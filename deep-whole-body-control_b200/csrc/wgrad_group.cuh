@@ -24,6 +24,17 @@ struct WGItem {
 };
 struct WGroup { int n, rows, slab, nslab; WGItem it[WG_MAX]; };
 
+// elect.sync: true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool wg_elect() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // X3 = error-compensated mode (3xTF32): a stage additionally holds the low parts G_lo = G - trunc_tf32(G), X_lo of its two
 // operand tiles (the tensor core truncates the 13 low mantissa bits of the raw tiles itself), chunks are 32 rows instead of 64 so
 // that three stages still fit, and every chunk is three accumulating MMA groups: G^T X + G_lo^T X + G^T X_lo.  The thread that
@@ -57,20 +68,27 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
     return (uint32_t)((c4 >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((c4 >> 1) & 3) ^ (k & 3)) << 5) + ((c4 & 1) << 4));
   };
   // chunk `cc` is the CTA-wide running chunk counter (stage cc % 3, use cc / 3): identical in every thread
-  auto fill_chunk = [&](const WGItem& g, int64_t k0, int nk, uint32_t cc, int pt) {
+  auto fill_chunk = [&](const WGItem& g, int64_t k0, int nk, uint32_t cc, int pt, bool first) {
     const int s = cc % 3;
-    asm volatile("bar.sync 4, 256;" ::: "memory");      // row-offset table of the previous chunk no longer read (and, at an item
-                                                        // boundary, the epilogue has released the stages it used as staging)
-    if (pt < WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
-    else if (pt >= 64 && pt < 64 + WCH) sh.rowoff[pt] = (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
+    // gathered operands (rows addressed through the mini-batch index) go through a row-offset table in shared memory, which costs two
+    // 256-thread barriers per chunk; plain row-major matrices and tile images compute the offset of a row arithmetically
+    const bool tabG = true, tabX = true;      // (computing the row address per 16-byte piece costs more issue slots than the two barriers: always use the table)
+    // (the first chunk of an item always synchronises: the epilogue warps used the stages as their staging tile until they got here)
+    if (tabG || tabX || first) asm volatile("bar.sync 4, 256;" ::: "memory");      // row-offset table of the previous chunk no longer read
+    if (tabG || tabX) {
+      if (pt < WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
+      else if (pt >= 64 && pt < 64 + WCH) sh.rowoff[pt] = (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
+    }
     tc_mbar_wait(&sh.empty[s], ((cc / 3) & 1) ^ 1);
-    asm volatile("bar.sync 4, 256;" ::: "memory");
+    if (tabG || tabX) asm volatile("bar.sync 4, 256;" ::: "memory");
     for (int op = 0; op < 2; ++op) {
       float* dst = wg_smem + s * STAGE + op * TILE;
-      const float* base = op == 0 ? g.G.p : g.X.p;
+      const RowMat& R = op == 0 ? g.G : g.X;
+      const float* base = R.p;
       const int64_t* ro = sh.rowoff + 64 * op;
+      const bool tab = op == 0 ? tabG : tabX;
       const int ncol = op == 0 ? g.Mo : g.Ni;
-      const int pst = (op == 0 ? g.G : g.X).image() ? 32 : 4;
+      const int pst = R.image() ? 32 : 4;
       if (op == 0 ? g.fastG : g.fastX) {
         const int cpr = ncol >> 2;                          // 16-byte pieces per row
         const uint32_t d0 = tc_smem_u32(dst);
@@ -78,14 +96,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
         const int sh2 = 31 - __clz(cpr);
         for (int i = pt; i < WCH * cpr; i += 256) {
           const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;          // row, piece
-          const float* src = k < nk ? base + ro[k] + pst * c4 : base;      // piece stride: 4 floats (row-major) or 32 (tile image)
+          const float* src = base;
+          if (k < nk) src = (tab ? base + ro[k] : R.row(k0 + k)) + pst * c4;       // piece stride: 4 floats (row-major) or 32 (tile image)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + piece_off(k, c4)), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
         }
       } else {
         for (int i = pt; i < WCH * ncol; i += 256) {
           const int k = i / ncol, f = i - k * ncol;
           const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
-          dst[off] = k < nk ? base[ro[k] + f] : 0.0f;
+          dst[off] = k < nk ? (tab ? base[ro[k] + f] : R.row(k0 + k)[f]) : 0.0f;
         }
       }
     }
@@ -125,7 +144,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
   auto fill_item = [&](const WGItem& g, int64_t k_begin, int64_t k_end, int nch, uint32_t cc, int pt, auto&& between) {
     for (int c = 0; c < nch; ++c) {
       const int64_t k0 = k_begin + (int64_t)c * WCH;
-      fill_chunk(g, k0, (int)min((int64_t)WCH, k_end - k0), cc + c, pt);
+      fill_chunk(g, k0, (int)min((int64_t)WCH, k_end - k0), cc + c, pt, c == 0);
       if (X3 && c > 0) {
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         split_chunk(g, cc + c - 1, pt);
@@ -149,29 +168,33 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
     if (warp < 4) {
       fill_item(g, k_begin, k_end, nch, cc, tid, [](int) {});
     } else if (warp == 4) {
-      if (lane == 0) {
-        const uint32_t idesc = tc_idesc(nipad, true, true);
-        for (int c = 0; c < nch; ++c) {
-          const uint32_t u = cc + c;
-          const int s = u % 3;
-          tc_mbar_wait(&sh.full[s], (u / 3) & 1);
-          tc_fence_async_smem();          // generic-proxy writes of the producers (made visible by the barrier) -> async proxy reads of the MMA
-          tc_fence_after();
-          const uint32_t a0 = tc_smem_u32(wg_smem + s * STAGE), b0 = a0 + TILE * 4;
-          for (int kk = 0; kk < WCH; kk += 8) {
-            const uint64_t ad = tc_desc(a0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
-            const uint64_t bd = tc_desc(b0 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
+      // the whole warp runs the loop (converged, warp-uniform values); the tcgen05 instructions sit under elect.sync -- issued from inside
+      // `if (lane == 0)` every tcgen05.mma was wrapped in an elect / R2UR.BROADCAST / branch loop (operands not provably uniform)
+      const uint32_t idesc = tc_idesc(nipad, true, true);
+      for (int c = 0; c < nch; ++c) {
+        const uint32_t u = cc + c;
+        const int s = u % 3;
+        tc_mbar_wait(&sh.full[s], (u / 3) & 1);
+        tc_fence_async_smem();          // generic-proxy writes of the producers (made visible by the barrier) -> async proxy reads of the MMA
+        tc_fence_after();
+        const uint32_t a0 = tc_smem_u32(wg_smem + s * STAGE), b0 = a0 + TILE * 4;
+        if (wg_elect()) {
+          uint64_t ad = tc_desc(a0, 512, 2048) | ((uint64_t)1 << 61), bd = tc_desc(b0, 512, 2048) | ((uint64_t)1 << 61);
+          uint64_t adl = tc_desc(a0 + 2 * TILE * 4, 512, 2048) | ((uint64_t)1 << 61), bdl = tc_desc(b0 + 2 * TILE * 4, 512, 2048) | ((uint64_t)1 << 61);
+#pragma unroll
+          for (int kk = 0; kk < WCH; kk += 8) {           // one K step = 8 rows = two 4-row atoms: +4096 bytes = +256 in the address field
             tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || kk > 0) ? 1u : 0u);
             if (X3) {
-              const uint64_t adl = tc_desc(a0 + 2 * TILE * 4 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
-              const uint64_t bdl = tc_desc(b0 + 2 * TILE * 4 + (kk >> 2) * 2048, 512, 2048) | ((uint64_t)1 << 61);
               tc_mma_tf32(tmem, adl, bd, idesc, 1u);
               tc_mma_tf32(tmem, ad, bdl, idesc, 1u);
+              adl += 256; bdl += 256;
             }
+            ad += 256; bd += 256;
           }
           tc_commit(&sh.empty[s]);
+          if (c + 1 == nch) tc_commit(&sh.tfull[0]);
         }
-        tc_commit(&sh.tfull[0]);
+        __syncwarp();
       }
     } else {
       const int et = tid - (T2_PROD + 32);             // 0..127: output feature whose bias gradient / accumulator row this thread owns
