@@ -25,7 +25,7 @@
 
 namespace dwbc {
 
-constexpr int V2_E = 32;
+constexpr int V2_E = 16;                 // envs per CTA: 16 so that TWO CTAs share an SM (one CTA's bulk loads / stores overlap the other's arithmetic)
 constexpr int V2_THREADS = 256;
 constexpr int V2_CW = 7;                 // compute warps; warp 7 issues the speculative bulk stores
 constexpr int V2_CT = V2_CW * 32;
@@ -199,7 +199,7 @@ __device__ void coop_resample_goal(const DwbcEnvCfg& cfg, const DwbcStepArgs& A,
 }
 
 template <int ND, int NA, int AH, int P, int H, int NPRIV>
-__global__ void __launch_bounds__(V2_THREADS, 1)
+__global__ void __launch_bounds__(V2_THREADS, 2)
 env_step_v2_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant__ DwbcEnvBuffers B, const __grid_constant__ DwbcStepArgs A) {
   using Ly = V2<ND, NA, AH, P, H, NPRIV>;
   constexpr int HP = Ly::HP, CFS = Ly::CFS;
@@ -622,7 +622,7 @@ env_step_v2_kernel(const __grid_constant__ DwbcEnvCfg cfg, const __grid_constant
   V2_TICK(3);
 
   // ---- 7. fix-up pass: rare events, one warp per flagged env ------------------------------------
-  const unsigned fix_list = __ballot_sync(FULL, (flags_s[lane] & (F_GOAL_RS | F_RESET)) != 0);   // same value in every warp
+  const unsigned fix_list = __ballot_sync(FULL, lane < V2_E && (flags_s[lane] & (F_GOAL_RS | F_RESET)) != 0);   // same value in every warp
   for (int k = wid; k < __popc(fix_list); k += V2_CW) {
     const int e = __fns(fix_list, 0, k + 1);    // k-th flagged env: flagged envs are dealt round-robin to the warps
     int flags = flags_s[e];
@@ -813,11 +813,11 @@ int dwbc_launch_env_step_v2(const DwbcEnvCfg* cfg, const DwbcEnvBuffers* buf, co
       cfg->num_priv != 24 || (cfg->sums_stride & 3) || cfg->n_collision_samples > 32)
     return DWBC_ERR_UNSUPPORTED;
   const size_t smem = (size_t)(K::o_sums + V2_E * cfg->sums_stride) * sizeof(float);
-  if (smem > 200 * 1024) return DWBC_ERR_UNSUPPORTED;
+  if (smem > 110 * 1024) return DWBC_ERR_UNSUPPORTED;      // two CTAs per SM
   auto kern = env_step_v2_kernel<20, 18, 4, 76, 10, 24>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DWBC_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) return DWBC_ERR_LAUNCH;
     attr_set = true;
   }
   kern<<<cfg->num_envs / V2_E, V2_THREADS, smem, st>>>(*cfg, *buf, *args);

@@ -10,6 +10,7 @@
 
 #include <stdlib.h>
 
+#include "hist_fused.cuh"
 #include "mlp_chain2.cuh"
 #include "wgrad_group.cuh"
 
@@ -225,6 +226,24 @@ static int hist_forward(const DwbcNetCfg& n, const float* P, const float* obs, c
   TRY(linear_fwd(a2, p.hw2, 40, P + n.off_hist_b[2], p.hc2, 12, rows * 3, 10, 40, ACT_ELU, 0, st));                                     // AC:60
   TRY(linear_fwd(rowmat(p.hc2, 36), p.hwl, 36, P + n.off_hist_b[3], p.zh, Lld, rows, L, 36, ACT_ELU, 0, st));                           // AC:72
   return DWBC_OK;
+}
+
+// history latent only (no intermediates kept): the fused exact-fp32 kernel on the tensor-core precisions (hist_fused.cuh), the layer-wise
+// GEMMs on the fp32 anchor path
+static int hist_latent_only(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows, const Plan& p,
+                            float* out, int64_t ld_out, cudaStream_t st) {
+  if (mlp_precision == 0 || (obs_stride & 3) || (reinterpret_cast<uintptr_t>(obs) & 15) || (n.num_prop & 3) || ((n.num_obs - n.num_hist * n.num_prop) & 3)) {
+    Plan q = p;
+    q.zh = out;
+    if (ld_out != align_up(p.latent, 4)) return DWBC_ERR_ARG;
+    return hist_forward(n, P, obs, idx, obs_stride, rows, q, st);
+  }
+  HistFusedArgs a{};
+  a.wp = P + n.off_hist_w[0]; a.bp = P + n.off_hist_b[0]; a.w1 = P + n.off_hist_w[1]; a.b1 = P + n.off_hist_b[1];
+  a.w2 = P + n.off_hist_w[2]; a.b2 = P + n.off_hist_b[2]; a.wl = P + n.off_hist_w[3]; a.bl = P + n.off_hist_b[3];
+  a.hist = rowmat_gather(obs + (n.num_obs - n.num_hist * n.num_prop), idx, obs_stride);
+  a.out = out; a.ld_out = ld_out; a.rows = rows; a.latent = p.latent;
+  return launch_hist_fused(a, st);
 }
 
 static int priv_forward(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, int rows,
@@ -712,7 +731,7 @@ extern "C" int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const
   const float* z;
   int zld = (int)align_up(p.latent, 4);
   if (chain_usable(n, p, obs, obs_stride)) {
-    if (hist_encoding) TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
+    if (hist_encoding) TRY(hist_latent_only(n, params, obs, nullptr, obs_stride, rows, p, p.zh, zld, st));
     C2PackList pl{};
     pl.out = p.wpack;
     int64_t off = 0;
@@ -762,8 +781,7 @@ extern "C" int dwbc_hist_latent(const DwbcNetCfg* net, const float* params, cons
   if (!params || !obs || !out || !workspace || rows <= 0) return DWBC_ERR_ARG;
   Plan p = make_plan(*net, rows, workspace);
   if (ld_out != align_up(p.latent, 4)) return DWBC_ERR_ARG;
-  p.zh = out;
-  return hist_forward(*net, params, obs, nullptr, obs_stride, rows, p, (cudaStream_t)stream);
+  return hist_latent_only(*net, params, obs, nullptr, obs_stride, rows, p, out, ld_out, (cudaStream_t)stream);
 }
 
 extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* params, const DwbcStorage* s, const int64_t* idx, int32_t M,
@@ -783,7 +801,7 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   // forward (the reference evaluates the actor 3x and the priv encoder 3x per mini-batch,
   // PPO:166,174,230; identical values, so each is evaluated once here)
   float* z = p.priv[n.n_priv_layers - 1];
-  if (!s->hist_latent) TRY(hist_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));           // PPO:175-176 (no grad)
+  if (!s->hist_latent) TRY(hist_latent_only(n, P, s->observations, idx, s->obs_stride, rows, p, p.zh, Lld, st));           // PPO:175-176 (no grad)
   if (chain_usable(n, p, s->observations, s->obs_stride)) {
     // tensor-core path: forward chains with the loss in the heads' epilogues, backward chains, grouped weight gradients.  The
     // weight images of all four programs are packed by ONE launch (the parameters are constant within a mini-batch).
