@@ -325,6 +325,10 @@ def run_ours(args):
     roll_ms = cuda_ms(roll, 3, barrier, device, world)
     gae_ms = cuda_ms(lambda: w.alg.compute_returns(w.obs), 3, barrier, device, world)
     upd_ms = cuda_ms(lambda: w.alg.update(), 3, barrier, device, world)
+    # ---- the one exchange step of the path: NCCL all-reduce of the flat gradient (675 KB), once per mini-batch ----
+    allreduce_us = None
+    if world > 1:
+        allreduce_us = 1e3 * cuda_ms(lambda: w.alg._allreduce(0, w.alg.actor_critic.num_params), 20, barrier, device, world)
     dag = None
     if args.config == "roa":
         w.dagger_iteration()
@@ -392,6 +396,9 @@ def run_ours(args):
             line["roa"] = dag
         if dist_parity:
             line["dist_parity"] = dist_parity
+        if allreduce_us is not None:
+            line["grad_allreduce"] = {"us_per_call": allreduce_us, "bytes": int(w.alg.actor_critic.num_params * 4), "calls_per_update": 20,
+                                      "note": "NCCL all-reduce of the flat gradient buffer, back to back (max over ranks); exposed between the weight-gradient kernel and clip+Adam"}
         torch.cuda.synchronize()
         if world == 1:
             line["reference_eager_b200"] = reference_eager_block(device, w.N, w.T, roll_ms, gae_ms, upd_ms, k1_ms * w.T)

@@ -58,7 +58,7 @@ class FusedPPO:
                  use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device="cuda:0",
                  mixing_schedule=(0.5, 2000, 4000), torque_supervision=False, torque_supervision_schedule=(0.1, 1000, 1000),
                  adaptive_arm_gains=False, min_policy_std=None, dagger_update_freq=20, priv_reg_coef_schedual=(0, 0, 0, 1),
-                 world_size=1, process_group=None, precision="fp32"):
+                 world_size=1, process_group=None, precision="tf32x3"):
         if torque_supervision or adaptive_arm_gains:
             raise L.DwbcError("torque_supervision / adaptive_arm_gains are disabled for widowGo1 (WGC:168,173) and outside the hot path")
         if schedule != "fixed":

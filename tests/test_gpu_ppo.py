@@ -21,6 +21,7 @@ def make_alg(N, T, P, **over):
     ac.load_state_dict(P)
     hp = ppo_hp()
     hp.update(over)
+    hp.setdefault("precision", "fp32")          # the CUDA-core anchor unless a test names a tensor-core mode
     alg = FusedPPO(ac, device="cuda:0", **hp)
     alg.init_storage(N, T, [860], [None], [18])
     return alg
