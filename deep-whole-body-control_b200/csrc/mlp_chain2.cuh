@@ -632,7 +632,18 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
       };
 
       uint32_t n = nop;
-      // ---- item start: both slots' initial loads ----
+      // ---- item start: the rows a LATER gather of this item will read are pulled into L2 now (its latency is exposed otherwise: the tile
+      // columns it fills are still in use), then both slots' initial loads ----
+      for (int l = 0; l < pr.n_loads; ++l) {
+        const C2Load& ld = pr.ld[l];
+        if (ld.before_op == 0 || ld.img) continue;
+        for (int s = 0; s < nslots; ++s) {
+          const int64_t m0 = (int64_t)(t0 + s) * TC_M;
+          if (m0 + lrow >= pr.M) continue;
+          const float* src = ld.src.row(m0 + lrow);
+          for (int b = lpc * 32; b < ld.ncols; b += LPS * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + b));
+        }
+      }
       do_loads(0, false);
       tc_fence_before();
       tc_fence_async_smem();

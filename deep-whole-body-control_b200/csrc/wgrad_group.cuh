@@ -15,6 +15,13 @@
 namespace dwbc {
 
 constexpr int WG_MAX = 20;
+// warp roles: WG_PW producer warps (operand copies), one MMA warp, four epilogue warps (which copy too, then bias sums / split-K reduction).
+// Eight producer warps instead of the four of gemm_tc2.cuh: the kernel is bound by the copy loop's issue rate and latency (warps active 14 %,
+// issue slots 28 % in the round-2 capture), and 13 warps x 137 registers still fit.
+constexpr int WG_PW = 8;
+constexpr int WG_PROD = 32 * WG_PW;               // producer threads
+constexpr int WG_FILL = WG_PROD + T2_EPI;         // threads that copy operand pieces (producers + epilogue warps)
+constexpr int WG_THREADS = WG_PROD + 32 + T2_EPI;
 struct WGItem {
   RowMat G, X;          // dZ [rows x Mo], X [rows x Ni]
   float* dW; int64_t lddw;
@@ -40,7 +47,7 @@ __device__ __forceinline__ bool wg_elect() {
 // that three stages still fit, and every chunk is three accumulating MMA groups: G^T X + G_lo^T X + G^T X_lo.  The thread that
 // copied a 16-byte piece also splits it (after cp.async.wait_group), one chunk behind its copies.
 template <bool X3>
-__global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid_constant__ WGroup grp) {
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid_constant__ WGroup grp) {
   extern __shared__ __align__(1024) float wg_smem[];
   __shared__ T2Shared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -49,13 +56,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
   constexpr int STAGE = (X3 ? 4 : 2) * TILE;        // {G, X} or {G, X, G_lo, X_lo}
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
-      tc_mbar_init(&sh.full[i], T2_PROD + T2_EPI);
+      tc_mbar_init(&sh.full[i], WG_FILL);
       tc_mbar_init(&sh.empty[i], 5);                // MMA commit + one lane of each of the 4 epilogue warps (bias-gradient reads)
     }
     tc_mbar_init(&sh.tfull[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tc_tmem_alloc(&sh.tmem_base, 128);
+  if (warp == WG_PW) tc_tmem_alloc(&sh.tmem_base, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -74,13 +81,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
     // 256-thread barriers per chunk; plain row-major matrices and tile images compute the offset of a row arithmetically
     const bool tabG = true, tabX = true;      // (computing the row address per 16-byte piece costs more issue slots than the two barriers: always use the table)
     // (the first chunk of an item always synchronises: the epilogue warps used the stages as their staging tile until they got here)
-    if (tabG || tabX || first) asm volatile("bar.sync 4, 256;" ::: "memory");      // row-offset table of the previous chunk no longer read
+    if (tabG || tabX || first) asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");      // row-offset table of the previous chunk no longer read
     if (tabG || tabX) {
       if (pt < WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
       else if (pt >= 64 && pt < 64 + WCH) sh.rowoff[pt] = (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
     }
     tc_mbar_wait(&sh.empty[s], ((cc / 3) & 1) ^ 1);
-    if (tabG || tabX) asm volatile("bar.sync 4, 256;" ::: "memory");
+    if (tabG || tabX) asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");
     for (int op = 0; op < 2; ++op) {
       float* dst = wg_smem + s * STAGE + op * TILE;
       const RowMat& R = op == 0 ? g.G : g.X;
@@ -94,14 +101,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
         const uint32_t d0 = tc_smem_u32(dst);
         const bool pow2 = (cpr & (cpr - 1)) == 0;
         const int sh2 = 31 - __clz(cpr);
-        for (int i = pt; i < WCH * cpr; i += 256) {
+        for (int i = pt; i < WCH * cpr; i += WG_FILL) {
           const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;          // row, piece
           const float* src = base;
           if (k < nk) src = (tab ? base + ro[k] : R.row(k0 + k)) + pst * c4;       // piece stride: 4 floats (row-major) or 32 (tile image)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + piece_off(k, c4)), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
         }
       } else {
-        for (int i = pt; i < WCH * ncol; i += 256) {
+        for (int i = pt; i < WCH * ncol; i += WG_FILL) {
           const int k = i / ncol, f = i - k * ncol;
           const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
           dst[off] = k < nk ? (tab ? base[ro[k] + f] : R.row(k0 + k)[f]) : 0.0f;
@@ -122,14 +129,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
         const int cpr = ncol >> 2;
         const bool pow2 = (cpr & (cpr - 1)) == 0;
         const int sh2 = 31 - __clz(cpr);
-        for (int i = pt; i < WCH * cpr; i += 256) {
+        for (int i = pt; i < WCH * cpr; i += WG_FILL) {
           const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;
           const uint32_t off = piece_off(k, c4) >> 2;
           const float4 v = *reinterpret_cast<const float4*>(src + off);
           *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
         }
       } else {
-        for (int i = pt; i < WCH * ncol; i += 256) {
+        for (int i = pt; i < WCH * ncol; i += WG_FILL) {
           const int k = i / ncol, f = i - k * ncol;
           const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
           dst[off] = tf32_lo(src[off]);
@@ -165,9 +172,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
     const int64_t k_end = min((int64_t)grp.rows, k_begin + grp.slab);
     const int nch = (int)((k_end - k_begin + WCH - 1) / WCH);
     const int Mo = g.Mo, Ni = g.Ni, nipad = (Ni + 15) & ~15;
-    if (warp < 4) {
+    if (warp < WG_PW) {
       fill_item(g, k_begin, k_end, nch, cc, tid, [](int) {});
-    } else if (warp == 4) {
+    } else if (warp == WG_PW) {
       // the whole warp runs the loop (converged, warp-uniform values); the tcgen05 instructions sit under elect.sync -- issued from inside
       // `if (lane == 0)` every tcgen05.mma was wrapped in an elect / R2UR.BROADCAST / branch loop (operands not provably uniform)
       const uint32_t idesc = tc_idesc(nipad, true, true);
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
         __syncwarp();
       }
     } else {
-      const int et = tid - (T2_PROD + 32);             // 0..127: output feature whose bias gradient / accumulator row this thread owns
+      const int et = tid - (WG_PROD + 32);             // 0..127: output feature whose bias gradient / accumulator row this thread owns
       const int q = warp & 3;
       float bsum = 0.0f;
       const int fo = (et >> 5) * 128 + (et & 7);       // float offset of feature et inside row 0 of its atom (before the chunk swizzle)
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
       };
       // bias sums of chunk c-1 right after the copies of chunk c were issued (X3: and chunk c-1 was split)
       int done = 0;                                     // chunks whose bias sums are taken
-      fill_item(g, k_begin, k_end, nch, cc, T2_PROD + et, [&](int c) {
+      fill_item(g, k_begin, k_end, nch, cc, WG_PROD + et, [&](int c) {
         while (done < c) { bias_chunk(cc + done); ++done; }      // chunks 0 .. c-1 have been handed over by this thread
       });
       while (done < nch) { bias_chunk(cc + done); ++done; }
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) wgrad_group_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tc_tmem_dealloc(tmem, 128);
+  if (warp == WG_PW) tc_tmem_dealloc(tmem, 128);
 }
 
 struct WGroupBuilder {
@@ -299,8 +306,8 @@ inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
       return DWBC_ERR_LAUNCH;
     attr = true;
   }
-  if (x3) wgrad_group_kernel<true><<<grid, T2_THREADS, smem, st>>>(g);
-  else wgrad_group_kernel<false><<<grid, T2_THREADS, smem, st>>>(g);
+  if (x3) wgrad_group_kernel<true><<<grid, WG_THREADS, smem, st>>>(g);
+  else wgrad_group_kernel<false><<<grid, WG_THREADS, smem, st>>>(g);
   ++dwbc_launch_counter;
   return cudaGetLastError() == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }

@@ -131,3 +131,34 @@ def test_default_params_equal_the_reference_config():
         if f.name in ("reward_scales", "arm_reward_scales"):
             a, b = nz(a), nz(b)
         assert a == b, (f.name, a, b)
+
+
+def test_fused_actor_critic_is_an_nn_module_over_the_flat_buffer():
+    """What OnPolicyRunner.__init__ needs from the policy object (OPR:63-91), checked without a GPU: reference constructor signature, nn.Module
+    parameters that alias the flat buffer, reference state_dict keys, .to() / .train(), every key of the reference's algorithm cfg accepted."""
+    import json
+    import os
+    import torch.nn as nn
+    from dwbc_b200 import runner_compat as RC
+    from dwbc_b200.ppo import FusedPPO
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = json.load(open(os.path.join(root, "baseline", "widowgo1_train_cfg.json")))
+    ac = RC.FusedActorCritic(76, 76, 18, **cfg["policy"], num_priv=24, num_hist=10, num_prop=76, device="cpu")
+    assert isinstance(ac, nn.Module) and ac.to("cpu") is ac and ac.train() is ac
+    assert sum(p.numel() for p in ac.parameters()) == 168698
+    keys = list(ac.state_dict())
+    assert keys[0] == "std" and "actor.history_encoder.conv_layers.2.weight" in keys and "critic.critic_arm_control_head.4.bias" in keys
+    ac.flat[ac.offsets["std"] + 3] = 0.5                                   # a kernel writing the flat buffer ...
+    assert float(next(iter(ac.parameters())).view(-1)[3]) == 0.5           # ... is what torch sees through the Parameter
+    sd = {k: v + 1.0 for k, v in ac.state_dict().items()}
+    ac.load_state_dict(sd)
+    assert abs(float(ac.std.view(-1)[3]) - 1.5) < 1e-6
+    alg = FusedPPO(ac, device="cpu", **cfg["algorithm"])
+    assert alg.actor_critic is ac and alg.precision == "tf32x3" and alg.actor_critic.net_cfg.precision == 2
+    alg.precision = "fp32"
+    assert ac.net_cfg.precision == 0
+
+    class Mod:
+        pass
+    names = RC.install(Mod)
+    assert Mod.FusedPPO is FusedPPO and Mod.FusedActorCritic is RC.FusedActorCritic and names["algorithm_class_name"] == "FusedPPO"
