@@ -28,8 +28,9 @@ __device__ __forceinline__ void t2_arrive(uint64_t* bar) {
 // tanh for the TF32 path: 1 - 2/(e^{2x}+1) with ex2.approx / rcp.approx (a few ulp; saturates correctly at +-inf). Short enough that an
 // if-converted activation select costs nothing for the ELU layers (precise tanhf is ~60 predicated instructions per element).
 __device__ __forceinline__ float t2_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
-__device__ __forceinline__ void t2_pbar() { asm volatile("bar.sync 2, %0;" ::"n"(T2_PROD) : "memory"); }   // producers only
-__device__ __forceinline__ void t2_ebar() { asm volatile("bar.sync 3, %0;" ::"n"(T2_EPI) : "memory"); }    // epilogue only
+// named barriers are the warp-aligned form: reconverge the warp first (a lane may still be behind a single-lane mbarrier arrive)
+__device__ __forceinline__ void t2_pbar() { __syncwarp(); asm volatile("bar.sync 2, %0;" ::"n"(T2_PROD) : "memory"); }   // producers only
+__device__ __forceinline__ void t2_ebar() { __syncwarp(); asm volatile("bar.sync 3, %0;" ::"n"(T2_EPI) : "memory"); }    // epilogue only
 
 // profiling aid: clock64 stamps of CTA events, [grid][64] (set with dwbc_debug_set_tc_cycle_buffer)
 __device__ unsigned long long* g_tc_cycles = nullptr;

@@ -203,7 +203,7 @@ __device__ __forceinline__ void c2_ld32_nowait(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void c2_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void c2_wbar() { asm volatile("bar.sync 1, %0;" ::"n"(C2_NW) : "memory"); }     // the sixteen worker warps
+__device__ __forceinline__ void c2_wbar() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(C2_NW) : "memory"); }     // the worker warps
 // hand-over of a worker warp: all its lanes have written (and fenced), ONE lane arrives (512 single-thread arrivals on one mbarrier
 // serialise to ~2 k cycles per op; 16 do not)
 __device__ __forceinline__ void c2_warp_arrive(uint64_t* bar, int lane) {
@@ -470,18 +470,23 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
       // tcgen05.mma in an elect / 7 x R2UR.BROADCAST / branch loop: ~300 cycles per MMA, i.e. the MMA thread, not the tensor core or the
       // epilogue, set the pace of the whole kernel.
       const uint32_t b0 = tc_smem_u32(wbuf);
-      auto fetch = [&](const float* img, uint32_t wbytes, uint32_t bbytes, uint32_t slot) {
+      // one tile per item (small batches: the rollout's act()): slot Y's tile is unused, so in 3xTF32 mode the low-part image of an op is
+      // fetched into it TOGETHER with the raw image instead of after the first two products (no serial second fetch per op)
+      const bool lo_side = x3 && L.pair == 1;
+      const uint32_t b0_lo = lo_side ? tc_smem_u32(tile[1]) : b0;
+      auto fetch = [&](const float* img, uint32_t wbytes, uint32_t bbytes, uint32_t slot, const float* img_lo = nullptr) {
         if (c2_elect()) {
-          c2_expect_tx(&sh.w_full, wbytes + bbytes);
+          c2_expect_tx(&sh.w_full, wbytes + bbytes + (img_lo ? wbytes : 0u));
           c2_bulk_g2s(wbuf, img, wbytes, &sh.w_full);
           if (bbytes) c2_bulk_g2s(bias_s + slot * 128, img + (wbytes >> 2), bbytes, &sh.w_full);
+          if (img_lo) c2_bulk_g2s(tile[1], img_lo, wbytes, &sh.w_full);
         }
         __syncwarp();
       };
       uint32_t n = nop;
       {
         const C2Op& o0 = pr.op[0];
-        fetch(o0.wp, (uint32_t)(o0.npad * o0.kpad) * 4u, (uint32_t)o0.npad * 4u, n & 1);
+        fetch(o0.wp, (uint32_t)(o0.npad * o0.kpad) * 4u, (uint32_t)o0.npad * 4u, n & 1, lo_side ? o0.wp_lo : nullptr);
       }
       for (int i = 0; i < nops; ++i, ++n) {
         const C2Op& o = pr.op[i];
@@ -515,6 +520,13 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
               uint32_t at = dt + 128 + o.a_col0;
 #pragma unroll 4
               for (int k = 0; k < nk; ++k, at += 8, bd += 16) c2_mma_ts(dt, at, bd, idesc, 1u);
+              if (lo_side) {                               // third product right away: the low-part image is already there
+                ad = tc_desc(a0, 128, 4096); bd = tc_desc(b0_lo, 128, wsbo);
+#pragma unroll 4
+                for (int k = 0; k < nk; ++k, ad += 16, bd += 16) tc_mma_tf32(dt, ad, bd, idesc, 1u);
+                if (reload_next) c2_bulk_wait_all(); else if (st_prev) c2_bulk_wait_read();
+                tc_commit(&sh.mma_done[s]);
+              }
             } else {
               if (reload_next) c2_bulk_wait_all(); else if (st_prev) c2_bulk_wait_read();
               tc_commit(&sh.mma_done[s]);
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         __syncwarp();
         tc_mbar_wait(&sh.w_free, nf & 1); ++nf;        // every MMA reading the image has retired: the buffer may be refilled
         if (lane == 0 && nop == 0 && i < 10) T2_STAMP(6 * i + 3);
-        if (x3) {
+        if (x3 && !lo_side) {
           fetch(o.wp_lo, (uint32_t)(o.npad * o.kpad) * 4u, 0u, 0);
           tc_mbar_wait(&sh.w_full, nw & 1); ++nw;
           for (int s = 0; s < nslots; ++s) {
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         }
         if (i + 1 < nops) {
           const C2Op& o1 = pr.op[i + 1];
-          fetch(o1.wp, (uint32_t)(o1.npad * o1.kpad) * 4u, (uint32_t)o1.npad * 4u, (n + 1) & 1);
+          fetch(o1.wp, (uint32_t)(o1.npad * o1.kpad) * 4u, (uint32_t)o1.npad * 4u, (n + 1) & 1, lo_side ? o1.wp_lo : nullptr);
         }
       }
       // the last op's tiles: every slot is handed back once more; an image output leaves now, and the tiles may be reloaded (next item)

@@ -81,12 +81,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
     // 256-thread barriers per chunk; plain row-major matrices and tile images compute the offset of a row arithmetically
     const bool tabG = true, tabX = true;      // (computing the row address per 16-byte piece costs more issue slots than the two barriers: always use the table)
     // (the first chunk of an item always synchronises: the epilogue warps used the stages as their staging tile until they got here)
+    // (bar.sync is the warp-aligned form: reconverge first -- lane 0 may still be behind its mbarrier arrive)
+    __syncwarp();
     if (tabG || tabX || first) asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");      // row-offset table of the previous chunk no longer read
     if (tabG || tabX) {
       if (pt < WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
       else if (pt >= 64 && pt < 64 + WCH) sh.rowoff[pt] = (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
     }
     tc_mbar_wait(&sh.empty[s], ((cc / 3) & 1) ^ 1);
+    __syncwarp();
     if (tabG || tabX) asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");
     for (int op = 0; op < 2; ++op) {
       float* dst = wg_smem + s * STAGE + op * TILE;
