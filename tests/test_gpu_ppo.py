@@ -361,10 +361,13 @@ def test_fused_chain_backward_matches_fp32_path_many_tiles(precision):
     assert lerr <= tol["loss"]
 
 
+DAGGER_TF32_TOL = dict(loss_rel=2e-3, param_rms=2e-5, param_max=8e-4)      # 2 x the errors measured on B200 (printed below)
+
+
 def test_dagger_update_tf32_path_within_stated_tolerance():
     """update_dagger (PPO:265-291) on the TF32 path: the history-encoder GEMMs run on gemm_tc2_kernel (forward, data gradient and the
-    MN-major weight gradient of the layer-wise kernel).  Against the reference's golden vectors; stated tolerance: loss 1 %, parameters
-    after the 20 Adam steps within 20 * lr = 4e-3."""
+    MN-major weight gradient of the layer-wise kernel).  Against the reference's golden vectors; tolerances = 2 x the measured errors
+    (RMS over the history-encoder parameters after the 20 Adam steps: a few entries with near-zero gradients move by up to lr per step)."""
     g = np.load(os.path.join(G, "ppo.npz"))
     N, T, seed, _ = [int(x) for x in g["meta"]]
     P = golden_params(g, seed)
@@ -377,9 +380,15 @@ def test_dagger_update_tf32_path_within_stated_tolerance():
     inp2 = synth.rollout_inputs(N, T, 860, seed + 1)
     alg.storage._obs_all.copy_(torch.from_numpy(inp2["obs"]).cuda())
     loss = alg.update_dagger(indices=torch.from_numpy(g["dag_perm"]).cuda().long())
-    assert abs(loss - float(g["dag_loss"][0])) < 1e-2 * abs(float(g["dag_loss"][0]))
     ref = _flat_ref(alg.actor_critic, g["dag_params"])
     got = alg.actor_critic.unflat(alg.actor_critic.flat)
+    hist = [n for n, _ in alg.actor_critic.manifest if n.startswith("actor.history_encoder.")]
+    d = torch.cat([(got[n].cpu() - ref[n]).reshape(-1) for n in hist])
+    e_loss = abs(loss - float(g["dag_loss"][0])) / abs(float(g["dag_loss"][0]))
+    e_rms, e_max = float(d.pow(2).mean().sqrt()), float(d.abs().max())
+    print(f"[tf32 dagger] measured: loss rel {e_loss:.3g}, history-encoder params after 20 steps rms {e_rms:.3g} max {e_max:.3g}")
     for n, _ in alg.actor_critic.manifest:
         assert torch.isfinite(got[n]).all(), n
-        np.testing.assert_allclose(got[n].cpu().numpy(), ref[n].numpy(), rtol=0, atol=4e-3, err_msg=n)
+        if n not in hist:
+            assert torch.equal(got[n].cpu(), ref[n]) or float((got[n].cpu() - ref[n]).abs().max()) < 1e-7, n    # update_dagger touches nothing else
+    assert e_loss < DAGGER_TF32_TOL["loss_rel"] and e_rms < DAGGER_TF32_TOL["param_rms"] and e_max < DAGGER_TF32_TOL["param_max"]
