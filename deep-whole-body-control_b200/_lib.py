@@ -71,7 +71,7 @@ class StepArgs(C.Structure):
     _fields_ = [("rand_uniform", vp), ("seed", u64), ("step", u64), ("do_push", i32),
                 ("lin_vel_x", f32 * 2), ("ang_vel_yaw", f32 * 2), ("goal_l", f32 * 2), ("goal_p", f32 * 2), ("goal_y", f32 * 2),
                 ("leg_scale", f32 * MAX_TERMS), ("arm_scale", f32 * MAX_TERMS),
-                ("leg_termination_scale", f32), ("arm_termination_scale", f32)]
+                ("leg_termination_scale", f32), ("arm_termination_scale", f32), ("generic_kernel", i32), ("reserved_", i32)]
 
 
 class NetCfg(C.Structure):

@@ -640,7 +640,7 @@ extern "C" int dwbc_post_physics_step(const DwbcEnvCfg* cfg, const DwbcEnvBuffer
       aligned16(buf->torques) && aligned16(buf->actions) && aligned16(buf->action_history) && aligned16(buf->mass_params) &&
       aligned16(buf->friction) && aligned16(buf->motor_strength) && aligned16(buf->goal_state) && aligned16(buf->derived_state) &&
       aligned16(buf->episode_length) && aligned16(buf->obs_history) && aligned16(buf->episode_sums) && aligned16(buf->obs_buf) &&
-      !getenv("DWBC_ENV_KERNEL_V1")) {
+      !args->generic_kernel) {
     int rc = dwbc_launch_env_step_v2(cfg, buf, args, (cudaStream_t)stream);
     if (rc != DWBC_ERR_UNSUPPORTED) return rc;
   }

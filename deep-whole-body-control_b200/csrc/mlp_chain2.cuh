@@ -905,11 +905,10 @@ inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fi
     if (pr.M <= 0 || pr.M != L.p[0].M || pr.n_ops <= 0 || pr.n_ops > C2_MAX_OPS || pr.n_loads < 0 || pr.n_loads > C2_MAX_LOADS) return DWBC_ERR_ARG;
   }
   if (!queue) return DWBC_ERR_ARG;
-  if (const char* dbg = getenv("DWBC_C2_DEBUG")) {      // timing experiments only (results invalid): 1 = drop every global activation store
-    if (atoi(dbg) & 1)
-      for (int k = 0; k < L.nprog; ++k)
-        for (int i = 0; i < L.p[k].n_ops; ++i) L.p[k].op[i].y = nullptr;
-  }
+#ifdef DWBC_C2_DROP_STORES      // timing experiments only (results invalid): no global activation stores
+  for (int k = 0; k < L.nprog; ++k)
+    for (int i = 0; i < L.p[k].n_ops; ++i) L.p[k].op[i].y = nullptr;
+#endif
   static int sms = 0;
   if (!sms) {
     int dev = 0;

@@ -42,24 +42,38 @@ __device__ __forceinline__ bool wg_elect() {
   return pred != 0;
 }
 
-// X3 = error-compensated mode (3xTF32): a stage additionally holds the low parts G_lo = G - trunc_tf32(G), X_lo of its two
-// operand tiles (the tensor core truncates the 13 low mantissa bits of the raw tiles itself), chunks are 32 rows instead of 64 so
-// that three stages still fit, and every chunk is three accumulating MMA groups: G^T X + G_lo^T X + G^T X_lo.  The thread that
-// copied a 16-byte piece also splits it (after cp.async.wait_group), one chunk behind its copies.
+struct WGShared {
+  uint64_t full[4], empty[4], lo_empty[2], tfull;
+  uint32_t tmem_base;
+  int64_t rowoff[2][128];      // row offsets (floats) of the chunk being copied and of the next one: [slot][0..63] = G rows, [64..127] = X rows
+};
+// the column piece a filling thread owns when WG_FILL is a multiple of the pieces per row: the row advances by `kstep` (a multiple of 4, so
+// the swizzle phase k & 3 is fixed) and the shared-memory address by a constant
+struct WGCol { int fixed, c4, k0, kstep; uint32_t doff, dstep; };
+
+// X3 = error-compensated mode (3xTF32): chunks are 32 rows; four raw stages {G, X} receive the cp.async copies, two more buffers hold the
+// low parts G_lo = G - trunc_tf32(G), X_lo of the chunk about to be multiplied (the tensor core truncates the 13 low mantissa bits of the
+// raw tiles itself), and every chunk is three accumulating MMA groups: G^T X + G_lo^T X + G^T X_lo.  The thread that copied a 16-byte
+// piece also splits it (after cp.async.wait_group), two chunks behind its copies, so ~96 KB of copies are in flight per SM.
 template <bool X3>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid_constant__ WGroup grp) {
   extern __shared__ __align__(1024) float wg_smem[];
-  __shared__ T2Shared sh;
+  __shared__ WGShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int WCH = X3 ? 32 : T2_WCH;             // rows per chunk
   constexpr int TILE = WCH * 128;                   // floats per operand tile: WCH rows x 128 features
-  constexpr int STAGE = (X3 ? 4 : 2) * TILE;        // {G, X} or {G, X, G_lo, X_lo}
+  constexpr int STAGE = 2 * TILE;                   // {G, X}
+  constexpr int NST = X3 ? 4 : 3;                   // raw stages
+  constexpr int AHEAD = 2;                          // X3: chunks the copies run ahead of the split
+  float* const lo_smem = wg_smem + NST * STAGE;     // X3: two {G_lo, X_lo} buffers
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < NST; ++i) {
       tc_mbar_init(&sh.full[i], WG_FILL);
       tc_mbar_init(&sh.empty[i], 5);                // MMA commit + one lane of each of the 4 epilogue warps (bias-gradient reads)
     }
-    tc_mbar_init(&sh.tfull[0], 1);
+    tc_mbar_init(&sh.lo_empty[0], 1);
+    tc_mbar_init(&sh.lo_empty[1], 1);
+    tc_mbar_init(&sh.tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WG_PW) tc_tmem_alloc(&sh.tmem_base, 128);
@@ -74,69 +88,87 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
   auto piece_off = [](int k, int c4) -> uint32_t {
     return (uint32_t)((c4 >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((c4 >> 1) & 3) ^ (k & 3)) << 5) + ((c4 & 1) << 4));
   };
-  // chunk `cc` is the CTA-wide running chunk counter (stage cc % 3, use cc / 3): identical in every thread
-  auto fill_chunk = [&](const WGItem& g, int64_t k0, int nk, uint32_t cc, int pt, bool first) {
-    const int s = cc % 3;
-    // gathered operands (rows addressed through the mini-batch index) go through a row-offset table in shared memory, which costs two
-    // 256-thread barriers per chunk; plain row-major matrices and tile images compute the offset of a row arithmetically
-    const bool tabG = true, tabX = true;      // (computing the row address per 16-byte piece costs more issue slots than the two barriers: always use the table)
-    // (the first chunk of an item always synchronises: the epilogue warps used the stages as their staging tile until they got here)
-    // (bar.sync is the warp-aligned form: reconverge first -- lane 0 may still be behind its mbarrier arrive)
-    __syncwarp();
-    if (tabG || tabX || first) asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");      // row-offset table of the previous chunk no longer read
-    if (tabG || tabX) {
-      if (pt < WCH) sh.rowoff[pt] = pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
-      else if (pt >= 64 && pt < 64 + WCH) sh.rowoff[pt] = (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
+  auto make_col = [&](int ncol, bool fast, int pt) -> WGCol {
+    WGCol f{};
+    const int cpr = ncol >> 2;
+    if (fast && cpr > 0 && WG_FILL % cpr == 0 && ((WG_FILL / cpr) & 3) == 0) {
+      f.fixed = 1; f.kstep = WG_FILL / cpr; f.k0 = pt / cpr; f.c4 = pt - f.k0 * cpr;
+      f.doff = piece_off(f.k0, f.c4); f.dstep = (uint32_t)(f.kstep >> 2) * 2048u;
     }
-    tc_mbar_wait(&sh.empty[s], ((cc / 3) & 1) ^ 1);
-    __syncwarp();
-    if (tabG || tabX) asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");
+    return f;
+  };
+  // row-offset table of chunk `c` of the item (rows k0 ..): gathered operands are addressed through the mini-batch index, one thread per row
+  // loads it; `pt` < 64 -> G rows, 64 <= pt < 128 -> X rows.  Returns the value, stored by the caller (after its copies were issued).
+  auto row_offset = [&](const WGItem& g, int64_t k0, int nk, int pt) -> int64_t {
+    if (pt < WCH) return pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
+    if (pt >= 64 && pt < 64 + WCH) return (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
+    return 0;
+  };
+  // copies of one chunk; `cc` is the CTA-wide running chunk counter (stage cc % NST, use cc / NST): identical in every thread
+  auto fill_chunk = [&](const WGItem& g, const WGCol (&col)[2], int nk, uint32_t cc, int slot, int pt) {
+    const int s = cc % NST;
+    tc_mbar_wait(&sh.empty[s], ((cc / NST) & 1) ^ 1);
     for (int op = 0; op < 2; ++op) {
       float* dst = wg_smem + s * STAGE + op * TILE;
       const RowMat& R = op == 0 ? g.G : g.X;
       const float* base = R.p;
-      const int64_t* ro = sh.rowoff + 64 * op;
-      const bool tab = op == 0 ? tabG : tabX;
+      const int64_t* ro = sh.rowoff[slot] + 64 * op;
       const int ncol = op == 0 ? g.Mo : g.Ni;
-      const int pst = R.image() ? 32 : 4;
+      const int pst = R.image() ? 32 : 4;                       // piece stride: 4 floats (row-major) or 32 (tile image)
       if (op == 0 ? g.fastG : g.fastX) {
-        const int cpr = ncol >> 2;                          // 16-byte pieces per row
         const uint32_t d0 = tc_smem_u32(dst);
-        const bool pow2 = (cpr & (cpr - 1)) == 0;
-        const int sh2 = 31 - __clz(cpr);
-        for (int i = pt; i < WCH * cpr; i += WG_FILL) {
-          const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;          // row, piece
-          const float* src = base;
-          if (k < nk) src = (tab ? base + ro[k] : R.row(k0 + k)) + pst * c4;       // piece stride: 4 floats (row-major) or 32 (tile image)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + piece_off(k, c4)), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
+        const WGCol& f = col[op];
+        if (f.fixed) {
+          const float* cb = base + pst * f.c4;
+          uint32_t d = d0 + f.doff;
+          for (int k = f.k0; k < WCH; k += f.kstep, d += f.dstep) {
+            const bool v = k < nk;
+            const float* src = v ? cb + ro[k] : base;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(v ? 16 : 0) : "memory");
+          }
+        } else {
+          const int cpr = ncol >> 2;                          // 16-byte pieces per row
+          for (int i = pt; i < WCH * cpr; i += WG_FILL) {
+            const int k = i / cpr, c4 = i - k * cpr;          // row, piece
+            const float* src = k < nk ? base + ro[k] + pst * c4 : base;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + piece_off(k, c4)), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
+          }
         }
       } else {
         for (int i = pt; i < WCH * ncol; i += WG_FILL) {
           const int k = i / ncol, f = i - k * ncol;
           const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
-          dst[off] = k < nk ? (tab ? base[ro[k] + f] : R.row(k0 + k)[f]) : 0.0f;
+          dst[off] = k < nk ? base[ro[k] + f] : 0.0f;
         }
       }
     }
     if (!X3) asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh.full[s])) : "memory");
     else asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  // X3: low parts of the pieces this thread copied into stage cc % 3 (its copies have landed: cp.async.wait_group before the call)
-  auto split_chunk = [&](const WGItem& g, uint32_t cc, int pt) {
-    const int s = cc % 3;
+  // X3: low parts of the pieces this thread copied into stage cc % NST (its copies have landed: cp.async.wait_group before the call)
+  auto split_chunk = [&](const WGItem& g, const WGCol (&col)[2], uint32_t cc, int pt) {
+    const int s = cc % NST, l = cc & 1;
+    tc_mbar_wait(&sh.lo_empty[l], ((cc >> 1) & 1) ^ 1);
     for (int op = 0; op < 2; ++op) {
-      float* src = wg_smem + s * STAGE + op * TILE;
-      float* dst = src + 2 * TILE;
+      const float* src = wg_smem + s * STAGE + op * TILE;
+      float* dst = lo_smem + l * STAGE + op * TILE;
       const int ncol = op == 0 ? g.Mo : g.Ni;
       if (op == 0 ? g.fastG : g.fastX) {
-        const int cpr = ncol >> 2;
-        const bool pow2 = (cpr & (cpr - 1)) == 0;
-        const int sh2 = 31 - __clz(cpr);
-        for (int i = pt; i < WCH * cpr; i += WG_FILL) {
-          const int k = pow2 ? (i >> sh2) : i / cpr, c4 = i - k * cpr;
-          const uint32_t off = piece_off(k, c4) >> 2;
-          const float4 v = *reinterpret_cast<const float4*>(src + off);
-          *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        const WGCol& f = col[op];
+        if (f.fixed) {
+          uint32_t off = f.doff >> 2;
+          for (int k = f.k0; k < WCH; k += f.kstep, off += f.dstep >> 2) {
+            const float4 v = *reinterpret_cast<const float4*>(src + off);
+            *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+          }
+        } else {
+          const int cpr = ncol >> 2;
+          for (int i = pt; i < WCH * cpr; i += WG_FILL) {
+            const int k = i / cpr, c4 = i - k * cpr;
+            const uint32_t off = piece_off(k, c4) >> 2;
+            const float4 v = *reinterpret_cast<const float4*>(src + off);
+            *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+          }
         }
       } else {
         for (int i = pt; i < WCH * ncol; i += WG_FILL) {
@@ -149,21 +181,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
     tc_fence_async_smem();
     t2_arrive(&sh.full[s]);
   };
-  // the fill schedule of one item for a filling thread: plain mode = fill every chunk (asynchronous arrival); X3 = copies run one
-  // chunk ahead of the split
+  // the fill schedule of one item for a filling thread.  Row-offset tables are double-buffered: the table of chunk c+1 is loaded (mini-batch
+  // index -> row offset, a global load) while the copies of chunk c are issued, and one CTA-wide barrier per chunk publishes it.
+  // `between(n)`: n = chunks this thread has completely handed over.
   auto fill_item = [&](const WGItem& g, int64_t k_begin, int64_t k_end, int nch, uint32_t cc, int pt, auto&& between) {
+    WGCol col[2] = {make_col(g.Mo, g.fastG, pt), make_col(g.Ni, g.fastX, pt)};
+    // (bar.sync is the warp-aligned form: reconverge first -- lane 0 may still be behind its mbarrier arrive)
+    __syncwarp();
+    asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // the epilogue warps used the stages as their staging tile until they got here; tables of the previous item no longer read
+    if (pt < 128) sh.rowoff[0][pt] = row_offset(g, k_begin, (int)min((int64_t)WCH, k_end - k_begin), pt);
     for (int c = 0; c < nch; ++c) {
       const int64_t k0 = k_begin + (int64_t)c * WCH;
-      fill_chunk(g, k0, (int)min((int64_t)WCH, k_end - k0), cc + c, pt, c == 0);
-      if (X3 && c > 0) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        split_chunk(g, cc + c - 1, pt);
+      __syncwarp();
+      asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // table c complete; table c-1 no longer read
+      int64_t nxt = 0;
+      const bool more = c + 1 < nch && pt < 128;
+      if (more) nxt = row_offset(g, k0 + WCH, (int)min((int64_t)WCH, k_end - k0 - WCH), pt);
+      fill_chunk(g, col, (int)min((int64_t)WCH, k_end - k0), cc + c, c & 1, pt);
+      if (more) sh.rowoff[(c + 1) & 1][pt] = nxt;
+      if (X3) {
+        if (c >= AHEAD) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
+          split_chunk(g, col, cc + c - AHEAD, pt);
+          between(c - AHEAD + 1);
+        }
+      } else {
+        between(c);
       }
-      between(c);
     }
-    if (X3 && nch > 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      split_chunk(g, cc + nch - 1, pt);
+    if (X3) {
+      for (int c = max(nch - AHEAD, 0); c < nch; ++c) {
+        if (nch - 1 - c >= 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        split_chunk(g, col, cc + c, pt);
+      }
     }
   };
 
@@ -183,14 +234,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
       const uint32_t idesc = tc_idesc(nipad, true, true);
       for (int c = 0; c < nch; ++c) {
         const uint32_t u = cc + c;
-        const int s = u % 3;
-        tc_mbar_wait(&sh.full[s], (u / 3) & 1);
+        const int s = u % NST;
+        tc_mbar_wait(&sh.full[s], (u / NST) & 1);
         tc_fence_async_smem();          // generic-proxy writes of the producers (made visible by the barrier) -> async proxy reads of the MMA
         tc_fence_after();
         const uint32_t a0 = tc_smem_u32(wg_smem + s * STAGE), b0 = a0 + TILE * 4;
+        const uint32_t al = tc_smem_u32(lo_smem + (u & 1) * STAGE), bl = al + TILE * 4;
         if (wg_elect()) {
           uint64_t ad = tc_desc(a0, 512, 2048) | ((uint64_t)1 << 61), bd = tc_desc(b0, 512, 2048) | ((uint64_t)1 << 61);
-          uint64_t adl = tc_desc(a0 + 2 * TILE * 4, 512, 2048) | ((uint64_t)1 << 61), bdl = tc_desc(b0 + 2 * TILE * 4, 512, 2048) | ((uint64_t)1 << 61);
+          uint64_t adl = tc_desc(al, 512, 2048) | ((uint64_t)1 << 61), bdl = tc_desc(bl, 512, 2048) | ((uint64_t)1 << 61);
 #pragma unroll
           for (int kk = 0; kk < WCH; kk += 8) {           // one K step = 8 rows = two 4-row atoms: +4096 bytes = +256 in the address field
             tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || kk > 0) ? 1u : 0u);
@@ -202,7 +254,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
             ad += 256; bd += 256;
           }
           tc_commit(&sh.empty[s]);
-          if (c + 1 == nch) tc_commit(&sh.tfull[0]);
+          if (X3) tc_commit(&sh.lo_empty[u & 1]);
+          if (c + 1 == nch) tc_commit(&sh.tfull);
         }
         __syncwarp();
       }
@@ -213,8 +266,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
       const int fo = (et >> 5) * 128 + (et & 7);       // float offset of feature et inside row 0 of its atom (before the chunk swizzle)
       const int c32 = (et & 31) >> 3;
       auto bias_chunk = [&](uint32_t u) {
-        const int s = u % 3;
-        tc_mbar_wait(&sh.full[s], (u / 3) & 1);
+        const int s = u % NST;
+        tc_mbar_wait(&sh.full[s], (u / NST) & 1);
         const float* gt = wg_smem + s * STAGE;
         if (g.db != nullptr && et < Mo) {
 #pragma unroll 8
@@ -223,16 +276,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
         __syncwarp();
         if (lane == 0) t2_arrive(&sh.empty[s]);
       };
-      // bias sums of chunk c-1 right after the copies of chunk c were issued (X3: and chunk c-1 was split)
+      // bias sums of the chunks this thread has handed over, between its copies
       int done = 0;                                     // chunks whose bias sums are taken
-      fill_item(g, k_begin, k_end, nch, cc, WG_PROD + et, [&](int c) {
-        while (done < c) { bias_chunk(cc + done); ++done; }      // chunks 0 .. c-1 have been handed over by this thread
+      fill_item(g, k_begin, k_end, nch, cc, WG_PROD + et, [&](int n) {
+        while (done < n) { bias_chunk(cc + done); ++done; }
       });
       while (done < nch) { bias_chunk(cc + done); ++done; }
       if (nch > 0) {
         if (g.db && et < Mo) atomicAdd(g.db + et, bsum);
         const int o = q * 32 + lane;
-        tc_mbar_wait(&sh.tfull[0], j & 1);
+        tc_mbar_wait(&sh.tfull, j & 1);
         tc_fence_after();
         t2_ebar();                                      // every epilogue warp is done reading G tiles (bias gradient) before the stages are reused
         // all MMAs of this item have completed and the producers wait at the next item's first bar.sync: the operand stages

@@ -104,7 +104,7 @@ class FusedWidowGo1Core:
     """Task state + fused post-physics step for one env shard on one GPU."""
 
     def __init__(self, p: WidowGo1Params, device="cuda:0", state: Optional[Dict[str, np.ndarray]] = None, seed: int = 0,
-                 sync_stats: bool = True):
+                 sync_stats: bool = True, generic_kernel: bool = False):
         self.p, self.cfg_params = p, p
         self.device = torch.device(device)
         self.num_envs, self.num_obs, self.num_actions = p.num_envs, p.num_obs, p.num_actions
@@ -162,6 +162,7 @@ class FusedWidowGo1Core:
         self._cfg = make_env_cfg(p, self._sums_stride)
         self._buf = L.EnvBuffers()
         self._args = L.StepArgs()
+        self._args.generic_kernel = int(generic_kernel)     # True: always the warp-per-env kernel (the fallback for odd N / unaligned buffers)
         self._leg_terms, self._arm_terms = p.active_terms("leg"), p.active_terms("arm")
         if state is not None:
             self.load_state(state)

@@ -185,6 +185,8 @@ typedef struct DwbcStepArgs {
   float lin_vel_x[2], ang_vel_yaw[2], goal_l[2], goal_p[2], goal_y[2]; /* (lo, span=hi-lo) */
   float leg_scale[DWBC_MAX_TERMS], arm_scale[DWBC_MAX_TERMS];         /* aligned with cfg.leg_term / arm_term */
   float leg_termination_scale, arm_termination_scale;                  /* 0 when inactive */
+  int32_t generic_kernel;        /* 1 = always run the warp-per-env kernel (any N / unaligned buffers), 0 = pick by shape */
+  int32_t reserved_;
 } DwbcStepArgs;
 
 /* Replaces WidowGo1.post_physics_step after its four gym.refresh_* calls (WG:875-910),

@@ -34,11 +34,11 @@ def load_sim(core, p, sim):
 
 
 @pytest.mark.parametrize("name", ["flat", "full"])
-def test_env_step_matches_reference_golden(name):
+def test_env_step_matches_reference_golden(name, generic_kernel=False):
     g = np.load(os.path.join(G, f"env_{name}.npz"))
     N, steps, seed, counter0 = [int(x) for x in g["meta"]]
     p = E.make_params(name, N)
-    core = make_core(p, E.initial(p, seed))
+    core = make_core(p, E.initial(p, seed), generic_kernel=generic_kernel)
     core.common_step_counter = counter0
     for t in range(1, steps + 1):
         i = t - 1
@@ -217,8 +217,7 @@ def test_torque_controller_matches_reference_golden():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["flat", "full"])
-def test_general_fallback_kernel_matches_reference_golden(name, monkeypatch):
+def test_general_fallback_kernel_matches_reference_golden(name):
     """`env_step_kernel` (warp per env; any N / n_dof / unaligned buffers) is what runs when the 32-envs-per-CTA TMA kernel does not
-    apply; DWBC_ENV_KERNEL_V1 forces it on the golden case."""
-    monkeypatch.setenv("DWBC_ENV_KERNEL_V1", "1")
-    test_env_step_matches_reference_golden(name)
+    apply; `DwbcStepArgs.generic_kernel` forces it on the golden case."""
+    test_env_step_matches_reference_golden(name, generic_kernel=True)

@@ -11,7 +11,7 @@ def main(name="flat", N=4096, iters=200, pool_n=40):
     p = E.make_params(name, N)
     st = synth.initial_env_state(p, 100); st.update(synth.sim_state(p, 100, 0, rp_sigma=0.05, z_lo=0.327))
     if p.measure_heights: st["height_samples"] = synth.height_field(p, 100)
-    env = FusedWidowGo1Core(p, "cuda:0", state=st, seed=1, sync_stats=False); env.update_command_curriculum()
+    env = FusedWidowGo1Core(p, "cuda:0", state=st, seed=1, sync_stats=False, generic_kernel=bool(os.environ.get("DWBC_ENV_KERNEL_V1"))); env.update_command_curriculum()
     base = {k: torch.from_numpy(v).cuda() for k, v in synth.sim_state(p, 100, 1, rp_sigma=0.05, z_lo=0.327).items()}
     pool = []
     for t in range(pool_n):
@@ -50,7 +50,7 @@ def phases(name="flat", N=4096):
     p = E.make_params(name, N)
     st = synth.initial_env_state(p, 100); st.update(synth.sim_state(p, 100, 0, rp_sigma=0.05, z_lo=0.327))
     if p.measure_heights: st["height_samples"] = synth.height_field(p, 100)
-    env = FusedWidowGo1Core(p, "cuda:0", state=st, seed=1, sync_stats=False); env.update_command_curriculum()
+    env = FusedWidowGo1Core(p, "cuda:0", state=st, seed=1, sync_stats=False, generic_kernel=bool(os.environ.get("DWBC_ENV_KERNEL_V1"))); env.update_command_curriculum()
     for _ in range(15): env.post_physics_step()
     buf = torch.zeros(N // 32 * 8, dtype=torch.int64, device="cuda")
     lib = L.lib(); lib.dwbc_debug_set_cycle_buffer.argtypes = [C.c_void_p]
@@ -73,7 +73,7 @@ def queued(name="flat", N=4096, n=40, reps=5):
     p = E.make_params(name, N)
     st = synth.initial_env_state(p, 100); st.update(synth.sim_state(p, 100, 0, rp_sigma=0.05, z_lo=0.327))
     if p.measure_heights: st["height_samples"] = synth.height_field(p, 100)
-    env = FusedWidowGo1Core(p, "cuda:0", state=st, seed=1, sync_stats=False); env.update_command_curriculum()
+    env = FusedWidowGo1Core(p, "cuda:0", state=st, seed=1, sync_stats=False, generic_kernel=bool(os.environ.get("DWBC_ENV_KERNEL_V1"))); env.update_command_curriculum()
     base = {k: torch.from_numpy(v).cuda() for k, v in synth.sim_state(p, 100, 1, rp_sigma=0.05, z_lo=0.327).items()}
     pool = []
     for t in range(n):
