@@ -15,13 +15,15 @@
 namespace dwbc {
 
 constexpr int WG_MAX = 20;
-// warp roles: WG_PW producer warps (operand copies), one MMA warp, four epilogue warps (which copy too, then bias sums / split-K reduction).
-// Eight producer warps instead of the four of gemm_tc2.cuh: the kernel is bound by the copy loop's issue rate and latency (warps active 14 %,
-// issue slots 28 % in the round-2 capture), and 13 warps x 137 registers still fit.
+// warp roles: WG_PW producer warps (operand copies; 3xTF32: and the low-part split), one MMA warp, four epilogue warps (bias-gradient column
+// sums of every chunk, then the split-K reduction of the accumulator).  The three roles only meet through mbarriers: the producers run up
+// to a whole stage ring ahead, the accumulator is double-buffered in tensor memory and the epilogue has its own staging tile, so the
+// copies of the next work item are in flight while the previous one is reduced.
 constexpr int WG_PW = 8;
 constexpr int WG_PROD = 32 * WG_PW;               // producer threads
-constexpr int WG_FILL = WG_PROD + T2_EPI;         // threads that copy operand pieces (producers + epilogue warps)
+constexpr int WG_FILL = WG_PROD;                  // threads that copy operand pieces
 constexpr int WG_THREADS = WG_PROD + 32 + T2_EPI;
+constexpr int WG_LDS = 36;                        // row stride (floats) of the epilogue staging tile [128][32 + 4]
 struct WGItem {
   RowMat G, X;          // dZ [rows x Mo], X [rows x Ni]
   float* dW; int64_t lddw;
@@ -43,7 +45,7 @@ __device__ __forceinline__ bool wg_elect() {
 }
 
 struct WGShared {
-  uint64_t full[4], empty[4], lo_empty[2], tfull;
+  uint64_t full[4], empty[4], lo_empty[2], tfull[2], tempty[2];
   uint32_t tmem_base;
   int64_t rowoff[2][128];      // row offsets (floats) of the chunk being copied and of the next one: [slot][0..63] = G rows, [64..127] = X rows
 };
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
   constexpr int NST = X3 ? 4 : 3;                   // raw stages
   constexpr int AHEAD = 2;                          // X3: chunks the copies run ahead of the split
   float* const lo_smem = wg_smem + NST * STAGE;     // X3: two {G_lo, X_lo} buffers
+  float* const stg = wg_smem + 6 * T2_WCH * 128;    // epilogue staging tile [128][WG_LDS], behind the 192 KB of operand buffers
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
       tc_mbar_init(&sh.full[i], WG_FILL);
@@ -73,10 +76,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
     }
     tc_mbar_init(&sh.lo_empty[0], 1);
     tc_mbar_init(&sh.lo_empty[1], 1);
-    tc_mbar_init(&sh.tfull, 1);
+    for (int i = 0; i < 2; ++i) { tc_mbar_init(&sh.tfull[i], 1); tc_mbar_init(&sh.tempty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == WG_PW) tc_tmem_alloc(&sh.tmem_base, 128);
+  if (warp == WG_PW) tc_tmem_alloc(&sh.tmem_base, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -181,14 +184,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
     tc_fence_async_smem();
     t2_arrive(&sh.full[s]);
   };
-  // the fill schedule of one item for a filling thread.  Row-offset tables are double-buffered: the table of chunk c+1 is loaded (mini-batch
-  // index -> row offset, a global load) while the copies of chunk c are issued, and one CTA-wide barrier per chunk publishes it.
-  // `between(n)`: n = chunks this thread has completely handed over.
-  auto fill_item = [&](const WGItem& g, int64_t k_begin, int64_t k_end, int nch, uint32_t cc, int pt, auto&& between) {
+  // the fill schedule of one item for a producer thread.  Row-offset tables are double-buffered: the table of chunk c+1 is loaded (mini-batch
+  // index -> row offset, a global load) while the copies of chunk c are issued, and one producer-wide barrier per chunk publishes it.
+  auto fill_item = [&](const WGItem& g, int64_t k_begin, int64_t k_end, int nch, uint32_t cc, int pt) {
     WGCol col[2] = {make_col(g.Mo, g.fastG, pt), make_col(g.Ni, g.fastX, pt)};
     // (bar.sync is the warp-aligned form: reconverge first -- lane 0 may still be behind its mbarrier arrive)
     __syncwarp();
-    asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // the epilogue warps used the stages as their staging tile until they got here; tables of the previous item no longer read
+    asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // tables of the previous item no longer read
     if (pt < 128) sh.rowoff[0][pt] = row_offset(g, k_begin, (int)min((int64_t)WCH, k_end - k_begin), pt);
     for (int c = 0; c < nch; ++c) {
       const int64_t k0 = k_begin + (int64_t)c * WCH;
@@ -199,14 +201,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
       if (more) nxt = row_offset(g, k0 + WCH, (int)min((int64_t)WCH, k_end - k0 - WCH), pt);
       fill_chunk(g, col, (int)min((int64_t)WCH, k_end - k0), cc + c, c & 1, pt);
       if (more) sh.rowoff[(c + 1) & 1][pt] = nxt;
-      if (X3) {
-        if (c >= AHEAD) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
-          split_chunk(g, col, cc + c - AHEAD, pt);
-          between(c - AHEAD + 1);
-        }
-      } else {
-        between(c);
+      if (X3 && c >= AHEAD) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
+        split_chunk(g, col, cc + c - AHEAD, pt);
       }
     }
     if (X3) {
@@ -227,11 +224,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
     const int nch = (int)((k_end - k_begin + WCH - 1) / WCH);
     const int Mo = g.Mo, Ni = g.Ni, nipad = (Ni + 15) & ~15;
     if (warp < WG_PW) {
-      fill_item(g, k_begin, k_end, nch, cc, tid, [](int) {});
+      fill_item(g, k_begin, k_end, nch, cc, tid);
     } else if (warp == WG_PW) {
       // the whole warp runs the loop (converged, warp-uniform values); the tcgen05 instructions sit under elect.sync -- issued from inside
       // `if (lane == 0)` every tcgen05.mma was wrapped in an elect / R2UR.BROADCAST / branch loop (operands not provably uniform)
       const uint32_t idesc = tc_idesc(nipad, true, true);
+      const uint32_t acc = tmem + (uint32_t)(j & 1) * 128;
+      if (nch > 0) {
+        tc_mbar_wait(&sh.tempty[j & 1], ((j >> 1) & 1) ^ 1);      // the epilogue of item j-2 has read this accumulator
+        tc_fence_after();
+      }
       for (int c = 0; c < nch; ++c) {
         const uint32_t u = cc + c;
         const int s = u % NST;
@@ -245,17 +247,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
           uint64_t adl = tc_desc(al, 512, 2048) | ((uint64_t)1 << 61), bdl = tc_desc(bl, 512, 2048) | ((uint64_t)1 << 61);
 #pragma unroll
           for (int kk = 0; kk < WCH; kk += 8) {           // one K step = 8 rows = two 4-row atoms: +4096 bytes = +256 in the address field
-            tc_mma_tf32(tmem, ad, bd, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+            tc_mma_tf32(acc, ad, bd, idesc, (c > 0 || kk > 0) ? 1u : 0u);
             if (X3) {
-              tc_mma_tf32(tmem, adl, bd, idesc, 1u);
-              tc_mma_tf32(tmem, ad, bdl, idesc, 1u);
+              tc_mma_tf32(acc, adl, bd, idesc, 1u);
+              tc_mma_tf32(acc, ad, bdl, idesc, 1u);
               adl += 256; bdl += 256;
             }
             ad += 256; bd += 256;
           }
           tc_commit(&sh.empty[s]);
           if (X3) tc_commit(&sh.lo_empty[u & 1]);
-          if (c + 1 == nch) tc_commit(&sh.tfull);
+          if (c + 1 == nch) tc_commit(&sh.tfull[j & 1]);
         }
         __syncwarp();
       }
@@ -276,49 +278,47 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
         __syncwarp();
         if (lane == 0) t2_arrive(&sh.empty[s]);
       };
-      // bias sums of the chunks this thread has handed over, between its copies
-      int done = 0;                                     // chunks whose bias sums are taken
-      fill_item(g, k_begin, k_end, nch, cc, WG_PROD + et, [&](int n) {
-        while (done < n) { bias_chunk(cc + done); ++done; }
-      });
-      while (done < nch) { bias_chunk(cc + done); ++done; }
+      for (int c = 0; c < nch; ++c) bias_chunk(cc + c);
       if (nch > 0) {
         if (g.db && et < Mo) atomicAdd(g.db + et, bsum);
         const int o = q * 32 + lane;
-        tc_mbar_wait(&sh.tfull, j & 1);
+        tc_mbar_wait(&sh.tfull[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        t2_ebar();                                      // every epilogue warp is done reading G tiles (bias gradient) before the stages are reused
-        // all MMAs of this item have completed and the producers wait at the next item's first bar.sync: the operand stages
-        // become the staging tile [128][132]; the split-K partial goes out as row-contiguous vector reductions
-        float* stg = wg_smem;
+        // split-K partial: 32 accumulator columns at a time through the staging tile (warp q owns rows q*32 .. q*32+31 of it), out as
+        // row-contiguous 128-byte vector reductions (eight lanes per row, four rows per instruction)
+        const bool v4 = (g.lddw & 3) == 0 && (Ni & 3) == 0 && (reinterpret_cast<uintptr_t>(g.dW) & 15) == 0;
+        const int rows_q = min(32, Mo - q * 32);
         for (int c0 = 0; c0 < nipad; c0 += 32) {
           float v[32];
-          tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+          tc_ld32(tmem + (uint32_t)(j & 1) * 128 + ((uint32_t)(q * 32) << 16) + c0, v);
+          __syncwarp();                                 // the previous column block's reads of the staging rows are done
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4)
-            *reinterpret_cast<float4*>(stg + (size_t)o * T2_LDS + c0 + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-        }
-        tc_fence_before();
-        __syncwarp();                                   // warp q wrote rows q*32 .. q*32+31 and reduces exactly those rows
-        const bool v4 = (g.lddw & 3) == 0 && (Ni & 3) == 0 && (reinterpret_cast<uintptr_t>(g.dW) & 15) == 0;
-        for (int r = q * 32; r < min(q * 32 + 32, Mo); ++r) {
-          float* crow = g.dW + (int64_t)r * g.lddw;
+            *reinterpret_cast<float4*>(stg + (size_t)o * WG_LDS + 4 * j4) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          __syncwarp();
           if (v4) {
-            if (4 * lane < Ni) {
-              const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)r * T2_LDS + 4 * lane);
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * lane), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+            const int cq = c0 + 4 * (lane & 7);
+            for (int r = lane >> 3; r < rows_q; r += 4) {
+              if (cq < Ni) {
+                const float4 a = *reinterpret_cast<const float4*>(stg + (size_t)(q * 32 + r) * WG_LDS + 4 * (lane & 7));
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g.dW + (int64_t)(q * 32 + r) * g.lddw + cq), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+              }
             }
           } else {
-            for (int n = lane; n < Ni; n += 32) atomicAdd(crow + n, stg[(size_t)r * T2_LDS + n]);
+            for (int r = 0; r < rows_q; ++r)
+              if (c0 + lane < Ni) atomicAdd(g.dW + (int64_t)(q * 32 + r) * g.lddw + c0 + lane, stg[(size_t)(q * 32 + r) * WG_LDS + lane]);
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) t2_arrive(&sh.tempty[j & 1]);
       }
     }
     cc += nch;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == WG_PW) tc_tmem_dealloc(tmem, 128);
+  if (warp == WG_PW) tc_tmem_dealloc(tmem, 256);
 }
 
 struct WGroupBuilder {
@@ -354,7 +354,7 @@ inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
   g.nslab = (int)((rows + slab - 1) / slab);
   const int items = g.n * g.nslab;
   const int grid = items < sms ? items : sms;
-  const size_t smem = (size_t)(6 * T2_WCH * 128) * sizeof(float);       // 3 stages x {G tile, X tile} = 192 KB (>= the 66 KB staging tile)
+  const size_t smem = (size_t)(6 * T2_WCH * 128 + 128 * WG_LDS) * sizeof(float);       // 192 KB of operand buffers + the 18 KB staging tile
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(wgrad_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
