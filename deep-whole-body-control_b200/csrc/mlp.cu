@@ -976,3 +976,6 @@ extern "C" int dwbc_debug_gemm(int mode, int tc, const float* A, int64_t lda, co
 extern "C" int dwbc_debug_set_tc_cycle_buffer(unsigned long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_tc_cycles, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }
+extern "C" int dwbc_debug_set_wg_cycle_buffer(unsigned long long* dev_ptr) {
+  return cudaMemcpyToSymbol(g_wg_cycles, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
+}

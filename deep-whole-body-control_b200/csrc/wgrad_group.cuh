@@ -19,10 +19,11 @@ constexpr int WG_MAX = 20;
 // sums of every chunk, then the split-K reduction of the accumulator).  The three roles only meet through mbarriers: the producers run up
 // to a whole stage ring ahead, the accumulator is double-buffered in tensor memory and the epilogue has its own staging tile, so the
 // copies of the next work item are in flight while the previous one is reduced.
-constexpr int WG_PW = 8;
+constexpr int WG_PW = 16;
 constexpr int WG_PROD = 32 * WG_PW;               // producer threads
 constexpr int WG_FILL = WG_PROD;                  // threads that copy operand pieces
 constexpr int WG_THREADS = WG_PROD + 32 + T2_EPI;
+constexpr int WG_KS32 = WG_FILL / 32;             // row step of a copy thread on a 128-wide operand (32 pieces per row)
 constexpr int WG_LDS = 36;                        // row stride (floats) of the epilogue staging tile [128][32 + 4]
 struct WGItem {
   RowMat G, X;          // dZ [rows x Mo], X [rows x Ni]
@@ -44,14 +45,19 @@ __device__ __forceinline__ bool wg_elect() {
   return pred != 0;
 }
 
+// profiling aid (tools/wgrad_profile.py): clock64 stamps of the CTA's second work item, [grid][64] (dwbc_debug_set_wg_cycle_buffer)
+__device__ unsigned long long* g_wg_cycles = nullptr;
+#define WG_STAMP(slot) do { if (g_wg_cycles && (slot) < 64) g_wg_cycles[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+
 struct WGShared {
   uint64_t full[4], empty[4], lo_empty[2], tfull[2], tempty[2];
   uint32_t tmem_base;
-  int64_t rowoff[2][128];      // row offsets (floats) of the chunk being copied and of the next one: [slot][0..63] = G rows, [64..127] = X rows
+  int64_t rowoff[2][128];      // (scalar-copied operands only) row offsets (floats) of the chunk being copied and of the next one: [slot][0..63] = G rows, [64..127] = X rows
 };
-// the column piece a filling thread owns when WG_FILL is a multiple of the pieces per row: the row advances by `kstep` (a multiple of 4, so
-// the swizzle phase k & 3 is fixed) and the shared-memory address by a constant
-struct WGCol { int fixed, c4, k0, kstep; uint32_t doff, dstep; };
+// the 16-byte column piece a copy thread owns in a vector-copied operand: the thread copies rows k0, k0 + WG_KS32, ... of every chunk (the
+// step is a multiple of 4, so the swizzle phase k & 3 and with it everything but a constant stride of the shared-memory address is fixed).
+// Row-major operand: a warp takes one whole row per instruction (c4 = lane, idle lanes past the row's width); tile image: 8 rows x 4 pieces.
+struct WGCol { int fixed, active, c4, k0; uint32_t doff; };
 
 // X3 = error-compensated mode (3xTF32): chunks are 32 rows; four raw stages {G, X} receive the cp.async copies, two more buffers hold the
 // low parts G_lo = G - trunc_tf32(G), X_lo of the chunk about to be multiplied (the tensor core truncates the 13 low mantissa bits of the
@@ -84,6 +90,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+  if (tid == 0) WG_STAMP(62);
   const int items = grp.n * grp.nslab;
   const int my_items = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -91,53 +98,78 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
   auto piece_off = [](int k, int c4) -> uint32_t {
     return (uint32_t)((c4 >> 3) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + ((((c4 >> 1) & 3) ^ (k & 3)) << 5) + ((c4 & 1) << 4));
   };
-  auto make_col = [&](int ncol, bool fast, int pt) -> WGCol {
+  constexpr int NR = WCH / WG_KS32;                 // rows of a chunk per copy thread and operand
+  constexpr uint32_t DSTEP = (WG_KS32 >> 2) * 2048; // shared-memory bytes between them
+  auto make_col = [&](int ncol, bool fast, bool image, int pt) -> WGCol {
     WGCol f{};
-    const int cpr = ncol >> 2;
-    if (fast && cpr > 0 && WG_FILL % cpr == 0 && ((WG_FILL / cpr) & 3) == 0) {
-      f.fixed = 1; f.kstep = WG_FILL / cpr; f.k0 = pt / cpr; f.c4 = pt - f.k0 * cpr;
-      f.doff = piece_off(f.k0, f.c4); f.dstep = (uint32_t)(f.kstep >> 2) * 2048u;
+    if (!fast) return f;                              // scalar copies through the row-offset table
+    f.fixed = 1;
+    if (image) {
+      // tile image: eight consecutive rows share each 128-byte line (row r at byte 16 * (r & 7) of piece c4's line), so a warp takes
+      // 8 rows x 4 pieces = four whole lines per copy instruction instead of 32 half-used sectors
+      static_assert(WG_FILL % 256 == 0 && 8 * (WG_FILL / 256) == WG_KS32, "image mapping");
+      f.k0 = (pt & 7) + 8 * (pt >> 8); f.c4 = (pt >> 3) & 31; f.active = 1;
+    } else {
+      f.k0 = pt >> 5; f.c4 = pt & 31; f.active = f.c4 < (ncol >> 2);
     }
+    f.doff = piece_off(f.k0, f.c4);
     return f;
   };
-  // row-offset table of chunk `c` of the item (rows k0 ..): gathered operands are addressed through the mini-batch index, one thread per row
-  // loads it; `pt` < 64 -> G rows, 64 <= pt < 128 -> X rows.  Returns the value, stored by the caller (after its copies were issued).
+  // byte offsets of this thread's rows of the chunk starting at row r0 (-1 = past the end of the slab: zero-filled).  For a gathered operand
+  // this is the load of the mini-batch index; it is issued one chunk ahead of its use.
+  auto rows_of = [&](const WGItem& g, const WGCol (&col)[2], int64_t r0, int64_t k_end, int64_t (&out)[2][NR]) {
+#pragma unroll
+    for (int op = 0; op < 2; ++op) {
+      const RowMat& R = op == 0 ? g.G : g.X;
+      const bool on = col[op].fixed && col[op].active;
+      const int64_t rb = r0 + col[op].k0;
+      if (R.rpg == 0) {                                // tile image (vector-copied operands have rpg <= 1: WGroupBuilder)
+#pragma unroll
+        for (int n = 0; n < NR; ++n) {
+          const int64_t r = rb + n * WG_KS32;
+          out[op][n] = (on && r < k_end) ? 4 * ((r >> 7) * 16384 + ((r & 127) >> 3) * 1024 + (r & 7) * 4) : -1;
+        }
+      } else {
+        const int64_t* idx = R.idx;
+        const int64_t sb = 4 * R.stride_g;
+#pragma unroll
+        for (int n = 0; n < NR; ++n) {
+          const int64_t r = rb + n * WG_KS32;
+          out[op][n] = (on && r < k_end) ? (idx ? idx[r] : r) * sb : -1;
+        }
+      }
+    }
+  };
+  // row-offset table (scalar-copied operands only) of the chunk starting at k0; `pt` < 64 -> G rows, 64 <= pt < 128 -> X rows
   auto row_offset = [&](const WGItem& g, int64_t k0, int nk, int pt) -> int64_t {
     if (pt < WCH) return pt < nk ? (g.G.row(k0 + pt) - g.G.p) : 0;
     if (pt >= 64 && pt < 64 + WCH) return (pt - 64) < nk ? (g.X.row(k0 + pt - 64) - g.X.p) : 0;
     return 0;
   };
   // copies of one chunk; `cc` is the CTA-wide running chunk counter (stage cc % NST, use cc / NST): identical in every thread
-  auto fill_chunk = [&](const WGItem& g, const WGCol (&col)[2], int nk, uint32_t cc, int slot, int pt) {
+  auto fill_chunk = [&](const WGItem& g, const WGCol (&col)[2], const int64_t (&rows)[2][NR], int nk, uint32_t cc, int slot, int pt) {
     const int s = cc % NST;
     tc_mbar_wait(&sh.empty[s], ((cc / NST) & 1) ^ 1);
+#pragma unroll
     for (int op = 0; op < 2; ++op) {
       float* dst = wg_smem + s * STAGE + op * TILE;
       const RowMat& R = op == 0 ? g.G : g.X;
       const float* base = R.p;
-      const int64_t* ro = sh.rowoff[slot] + 64 * op;
-      const int ncol = op == 0 ? g.Mo : g.Ni;
-      const int pst = R.image() ? 32 : 4;                       // piece stride: 4 floats (row-major) or 32 (tile image)
-      if (op == 0 ? g.fastG : g.fastX) {
-        const uint32_t d0 = tc_smem_u32(dst);
-        const WGCol& f = col[op];
-        if (f.fixed) {
-          const float* cb = base + pst * f.c4;
-          uint32_t d = d0 + f.doff;
-          for (int k = f.k0; k < WCH; k += f.kstep, d += f.dstep) {
-            const bool v = k < nk;
-            const float* src = v ? cb + ro[k] : base;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(v ? 16 : 0) : "memory");
-          }
-        } else {
-          const int cpr = ncol >> 2;                          // 16-byte pieces per row
-          for (int i = pt; i < WCH * cpr; i += WG_FILL) {
-            const int k = i / cpr, c4 = i - k * cpr;          // row, piece
-            const float* src = k < nk ? base + ro[k] + pst * c4 : base;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + piece_off(k, c4)), "l"(src), "r"(k < nk ? 16 : 0) : "memory");
+      const WGCol& f = col[op];
+      if (f.fixed) {
+        if (f.active) {
+          const char* cb = reinterpret_cast<const char*>(base + (R.image() ? 32 : 4) * f.c4);     // piece stride: 4 floats (row-major) or 32 (tile image)
+          const uint32_t d = tc_smem_u32(dst) + f.doff;
+#pragma unroll
+          for (int n = 0; n < NR; ++n) {
+            const int64_t o = rows[op][n];
+            const bool v = o >= 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + n * DSTEP), "l"(v ? cb + o : reinterpret_cast<const char*>(base)), "r"(v ? 16 : 0) : "memory");
           }
         }
       } else {
+        const int64_t* ro = sh.rowoff[slot] + 64 * op;
+        const int ncol = op == 0 ? g.Mo : g.Ni;
         for (int i = pt; i < WCH * ncol; i += WG_FILL) {
           const int k = i / ncol, f = i - k * ncol;
           const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
@@ -152,28 +184,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
   auto split_chunk = [&](const WGItem& g, const WGCol (&col)[2], uint32_t cc, int pt) {
     const int s = cc % NST, l = cc & 1;
     tc_mbar_wait(&sh.lo_empty[l], ((cc >> 1) & 1) ^ 1);
+#pragma unroll
     for (int op = 0; op < 2; ++op) {
       const float* src = wg_smem + s * STAGE + op * TILE;
       float* dst = lo_smem + l * STAGE + op * TILE;
-      const int ncol = op == 0 ? g.Mo : g.Ni;
-      if (op == 0 ? g.fastG : g.fastX) {
-        const WGCol& f = col[op];
-        if (f.fixed) {
-          uint32_t off = f.doff >> 2;
-          for (int k = f.k0; k < WCH; k += f.kstep, off += f.dstep >> 2) {
-            const float4 v = *reinterpret_cast<const float4*>(src + off);
-            *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-          }
-        } else {
-          const int cpr = ncol >> 2;
-          for (int i = pt; i < WCH * cpr; i += WG_FILL) {
-            const int k = i / cpr, c4 = i - k * cpr;
-            const uint32_t off = piece_off(k, c4) >> 2;
-            const float4 v = *reinterpret_cast<const float4*>(src + off);
-            *reinterpret_cast<float4*>(dst + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      const WGCol& f = col[op];
+      if (f.fixed) {
+        if (f.active) {
+          const float* sp = src + (f.doff >> 2);
+          float* dp = dst + (f.doff >> 2);
+#pragma unroll
+          for (int n = 0; n < NR; ++n) {
+            const float4 v = *reinterpret_cast<const float4*>(sp + n * (DSTEP >> 2));
+            *reinterpret_cast<float4*>(dp + n * (DSTEP >> 2)) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
           }
         }
       } else {
+        const int ncol = op == 0 ? g.Mo : g.Ni;
         for (int i = pt; i < WCH * ncol; i += WG_FILL) {
           const int k = i / ncol, f = i - k * ncol;
           const int off = ((f >> 5) * 512 + (k >> 2) * 2048 + (k & 3) * 128 + (((((f & 31) >> 3)) ^ (k & 3)) << 5) + ((f & 7) << 2)) >> 2;
@@ -184,27 +211,42 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
     tc_fence_async_smem();
     t2_arrive(&sh.full[s]);
   };
-  // the fill schedule of one item for a producer thread.  Row-offset tables are double-buffered: the table of chunk c+1 is loaded (mini-batch
-  // index -> row offset, a global load) while the copies of chunk c are issued, and one producer-wide barrier per chunk publishes it.
-  auto fill_item = [&](const WGItem& g, int64_t k_begin, int64_t k_end, int nch, uint32_t cc, int pt) {
-    WGCol col[2] = {make_col(g.Mo, g.fastG, pt), make_col(g.Ni, g.fastX, pt)};
-    // (bar.sync is the warp-aligned form: reconverge first -- lane 0 may still be behind its mbarrier arrive)
-    __syncwarp();
-    asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // tables of the previous item no longer read
-    if (pt < 128) sh.rowoff[0][pt] = row_offset(g, k_begin, (int)min((int64_t)WCH, k_end - k_begin), pt);
+  // the copy schedule of one item for a producer thread.  Vector-copied operands need no synchronisation among the producers: every thread
+  // addresses its own rows (their offsets fetched one chunk ahead).  Only an item with a scalar-copied operand (a width that is not a
+  // multiple of 4, or unaligned rows) goes through the shared row-offset table, double-buffered, one producer-wide barrier per chunk.
+  auto fill_item = [&](const WGItem& g, int64_t k_begin, int64_t k_end, int nch, uint32_t cc, int pt, bool stamp) {
+    const WGCol col[2] = {make_col(g.Mo, g.fastG, g.G.image(), pt), make_col(g.Ni, g.fastX, g.X.image(), pt)};
+    const bool table = !g.fastG || !g.fastX;
+    int64_t cur[2][NR], nx[2][NR];
+    rows_of(g, col, k_begin, k_end, cur);
+    if (table) {
+      // (bar.sync is the warp-aligned form: reconverge first -- lane 0 may still be behind its mbarrier arrive)
+      __syncwarp();
+      asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // tables of the previous item no longer read
+      if (pt < 128) sh.rowoff[0][pt] = row_offset(g, k_begin, (int)min((int64_t)WCH, k_end - k_begin), pt);
+    }
     for (int c = 0; c < nch; ++c) {
       const int64_t k0 = k_begin + (int64_t)c * WCH;
-      __syncwarp();
-      asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // table c complete; table c-1 no longer read
-      int64_t nxt = 0;
-      const bool more = c + 1 < nch && pt < 128;
-      if (more) nxt = row_offset(g, k0 + WCH, (int)min((int64_t)WCH, k_end - k0 - WCH), pt);
-      fill_chunk(g, col, (int)min((int64_t)WCH, k_end - k0), cc + c, c & 1, pt);
-      if (more) sh.rowoff[(c + 1) & 1][pt] = nxt;
+      int64_t tnext = 0;
+      const bool more = table && c + 1 < nch && pt < 128;
+      if (table) {
+        __syncwarp();
+        asm volatile("bar.sync 4, %0;" ::"n"(WG_FILL) : "memory");   // table c complete; table c-1 no longer read
+        if (more) tnext = row_offset(g, k0 + WCH, (int)min((int64_t)WCH, k_end - k0 - WCH), pt);
+      }
+      if (c + 1 < nch) rows_of(g, col, k0 + WCH, k_end, nx);
+      fill_chunk(g, col, cur, (int)min((int64_t)WCH, k_end - k0), cc + c, c & 1, pt);
+      if (more) sh.rowoff[(c + 1) & 1][pt] = tnext;
+      if (stamp && c < 12) WG_STAMP(c);
       if (X3 && c >= AHEAD) {
         asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
         split_chunk(g, col, cc + c - AHEAD, pt);
+        if (stamp && c - AHEAD < 12) WG_STAMP(12 + c - AHEAD);
       }
+#pragma unroll
+      for (int op = 0; op < 2; ++op)
+#pragma unroll
+        for (int n = 0; n < NR; ++n) cur[op][n] = nx[op][n];
     }
     if (X3) {
       for (int c = max(nch - AHEAD, 0); c < nch; ++c) {
@@ -224,7 +266,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
     const int nch = (int)((k_end - k_begin + WCH - 1) / WCH);
     const int Mo = g.Mo, Ni = g.Ni, nipad = (Ni + 15) & ~15;
     if (warp < WG_PW) {
-      fill_item(g, k_begin, k_end, nch, cc, tid);
+      if (tid == 0 && j == 1) WG_STAMP(60);
+      fill_item(g, k_begin, k_end, nch, cc, tid, tid == 0 && j == 1);
     } else if (warp == WG_PW) {
       // the whole warp runs the loop (converged, warp-uniform values); the tcgen05 instructions sit under elect.sync -- issued from inside
       // `if (lane == 0)` every tcgen05.mma was wrapped in an elect / R2UR.BROADCAST / branch loop (operands not provably uniform)
@@ -240,6 +283,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
         tc_mbar_wait(&sh.full[s], (u / NST) & 1);
         tc_fence_async_smem();          // generic-proxy writes of the producers (made visible by the barrier) -> async proxy reads of the MMA
         tc_fence_after();
+        if (lane == 0 && j == 1 && c < 12) WG_STAMP(24 + c);
         const uint32_t a0 = tc_smem_u32(wg_smem + s * STAGE), b0 = a0 + TILE * 4;
         const uint32_t al = tc_smem_u32(lo_smem + (u & 1) * STAGE), bl = al + TILE * 4;
         if (wg_elect()) {
@@ -258,6 +302,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
           tc_commit(&sh.empty[s]);
           if (X3) tc_commit(&sh.lo_empty[u & 1]);
           if (c + 1 == nch) tc_commit(&sh.tfull[j & 1]);
+          if (j == 1 && c < 12) WG_STAMP(36 + c);
         }
         __syncwarp();
       }
@@ -272,13 +317,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
         tc_mbar_wait(&sh.full[s], (u / NST) & 1);
         const float* gt = wg_smem + s * STAGE;
         if (g.db != nullptr && et < Mo) {
-#pragma unroll 8
-          for (int k = 0; k < WCH; ++k) bsum += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
+          // four independent partial sums (one per row of the 4-row atoms): the loads of a chunk are all in flight before the first add
+          float p4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+          for (int k = 0; k < WCH; ++k) p4[k & 3] += gt[fo + (k >> 2) * 512 + (k & 3) * 32 + ((c32 ^ (k & 3)) << 3)];
+          bsum += (p4[0] + p4[1]) + (p4[2] + p4[3]);
         }
         __syncwarp();
         if (lane == 0) t2_arrive(&sh.empty[s]);
       };
-      for (int c = 0; c < nch; ++c) bias_chunk(cc + c);
+      for (int c = 0; c < nch; ++c) {
+        bias_chunk(cc + c);
+        if (et == 0 && j == 1 && c < 12) WG_STAMP(48 + c);
+      }
       if (nch > 0) {
         if (g.db && et < Mo) atomicAdd(g.db + et, bsum);
         const int o = q * 32 + lane;
@@ -318,6 +369,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) WG_STAMP(63);
   if (warp == WG_PW) tc_tmem_dealloc(tmem, 256);
 }
 
@@ -328,8 +380,8 @@ struct WGroupBuilder {
     if (g.n >= WG_MAX || Mo > 128 || Ni > 128 || Mo <= 0 || Ni <= 0) { ok = false; return; }
     WGItem& it = g.it[g.n++];
     it.G = G; it.X = X; it.dW = dW; it.lddw = lddw; it.db = db; it.Mo = Mo; it.Ni = Ni;
-    it.fastG = rowmat_vec_ok(G) && (Mo & 3) == 0;
-    it.fastX = rowmat_vec_ok(X) && (Ni & 3) == 0;
+    it.fastG = rowmat_vec_ok(G) && (Mo & 3) == 0 && G.rpg <= 1;
+    it.fastX = rowmat_vec_ok(X) && (Ni & 3) == 0 && X.rpg <= 1;
     if ((G.rpg == 0 && !it.fastG) || (X.rpg == 0 && !it.fastX)) ok = false;      // tile images are always read in 16-byte pieces
   }
 };
