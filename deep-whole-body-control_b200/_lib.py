@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdwbc.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_DOF, MAX_TERMS, MAX_IDX, MAX_SLOTS, NUM_METRICS, RAND_COLS, MAX_LAYERS = 24, 40, 8, 64, 10, 104, 4
 GS, DS = 28, 72
 GS_COL = dict(commands=0, goal_timer=3, traj_timesteps=4, traj_total_timesteps=5, ee_start_sphere=6, ee_goal_sphere=9,
@@ -103,12 +103,14 @@ PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 class PpoHyper(C.Structure):
     _fields_ = [("clip_param", f32), ("value_loss_coef", f32), ("entropy_coef", f32), ("priv_reg_coef", f32),
                 ("mixing_ratio", f32), ("use_clipped_value_loss", i32), ("max_grad_norm", f32), ("lr", f32),
-                ("beta1", f32), ("beta2", f32), ("adam_eps", f32), ("grad_scale", f32)]
+                ("beta1", f32), ("beta2", f32), ("adam_eps", f32), ("grad_scale", f32),
+                ("torque_supervision_weight", f32), ("arm_coefs", vp)]
 
 
 class Storage(C.Structure):
     _fields_ = [("observations", vp), ("obs_stride", i64), ("actions", vp), ("values", vp), ("returns", vp),
-                ("advantages", vp), ("log_prob", vp), ("hist_latent", vp), ("hist_latent_ld", i64)]
+                ("advantages", vp), ("log_prob", vp), ("hist_latent", vp), ("hist_latent_ld", i64),
+                ("target_arm_torques", vp), ("current_arm_dof_pos", vp), ("current_arm_dof_vel", vp)]
 
 
 class PdCfg(C.Structure):

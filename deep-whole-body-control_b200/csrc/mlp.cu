@@ -425,15 +425,16 @@ struct LossArgs {
   int rows, n_leg, n_act, latent;
   float clip, c_value, c_ent, c_reg, rho;
   int clipped_value;
+  const float* ts_target; const float* ts_pos; const float* ts_vel; const float* ts_coef; float ts_w;      // arm torque supervision (PPO:224-239)
 };
 
 __global__ void __launch_bounds__(128) ppo_loss_kernel(const LossArgs a) {
-  __shared__ float red[4][4];
+  __shared__ float red[5][4];
   __shared__ float sred[32];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool on = r < a.rows;
   const float inv2m = 1.0f / (2.0f * (float)a.rows), invm = 1.0f / (float)a.rows;
-  float l_surr = 0.0f, l_val = 0.0f, l_reg = 0.0f, l_ent = 0.0f;
+  float l_surr = 0.0f, l_val = 0.0f, l_reg = 0.0f, l_ent = 0.0f, l_ts = 0.0f;
   float gstd[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) gstd[i] = 0.0f;
@@ -470,7 +471,16 @@ __global__ void __launch_bounds__(128) ppo_loss_kernel(const LossArgs a) {
       if (i < a.n_act) {
         const float sg = a.std[i], d = act[i] - mu[i];
         const int c = i < a.n_leg ? 0 : 1;
-        const float gmu = glp[c] * d / (sg * sg) * (1.0f - mu[i] * mu[i]);         // through tanh (AC:157,170)
+        float gmu = glp[c] * d / (sg * sg) * (1.0f - mu[i] * mu[i]);               // through tanh (AC:157,170)
+        if (c == 1 && a.ts_target != nullptr) {
+          // arm torque supervision: tau = kp (mu + q_default - q) - kd qd (PPO:318-323), loss w * mean((tau - target)^2) (PPO:236-238)
+          const int n_arm = a.n_act - a.n_leg, j = i - a.n_leg;
+          const float kp = a.ts_coef[j];
+          const float e = kp * (mu[i] + a.ts_coef[2 * n_arm + j] - a.ts_pos[src * n_arm + j]) - a.ts_coef[n_arm + j] * a.ts_vel[src * n_arm + j] -
+                          a.ts_target[src * n_arm + j];
+          l_ts += e * e;
+          gmu += 2.0f * a.ts_w / ((float)a.rows * (float)n_arm) * e * kp * (1.0f - mu[i] * mu[i]);
+        }
         if (c == 0) a.g_leg[(int64_t)r * a.gleg_ld + i] = gmu;
         else a.g_arm[(int64_t)r * a.garm_ld + (i - a.n_leg)] = gmu;
         gstd[i] = glp[c] * ((d * d) / (sg * sg * sg) - 1.0f / sg) - a.c_ent * inv2m / sg;
@@ -517,15 +527,15 @@ __global__ void __launch_bounds__(128) ppo_loss_kernel(const LossArgs a) {
   }
   // block reductions -> one atomic per CTA per quantity
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float v4[4] = {l_surr * inv2m, l_val * inv2m, l_reg * invm, l_ent * inv2m};
+  float v4[5] = {l_surr * inv2m, l_val * inv2m, l_reg * invm, l_ent * inv2m, l_ts * invm / (float)max(a.n_act - a.n_leg, 1)};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 5; ++k) {
     float s = warp_sum(v4[k]);
     if (lane == 0) red[k][w] = s;
   }
   if (threadIdx.x < 32) sred[threadIdx.x] = 0.0f;
   __syncthreads();
-  if (threadIdx.x < 4) atomicAdd(a.losses + threadIdx.x, (red[threadIdx.x][0] + red[threadIdx.x][1]) + (red[threadIdx.x][2] + red[threadIdx.x][3]));
+  if (threadIdx.x < (a.ts_target != nullptr ? 5 : 4)) atomicAdd(a.losses + threadIdx.x, (red[threadIdx.x][0] + red[threadIdx.x][1]) + (red[threadIdx.x][2] + red[threadIdx.x][3]));
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     if (i < a.n_act) {
@@ -789,6 +799,8 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   TRY(check_net(net));
   if (!params || !s || !idx || !hp || !grad || !losses_out || !workspace || M <= 0) return DWBC_ERR_ARG;
   if (!s->observations || !s->actions || !s->values || !s->returns || !s->advantages || !s->log_prob) return DWBC_ERR_ARG;
+  // torque supervision is on when the storage carries its three tensors (RS:82-84); then the arm coefficients are needed too
+  if (s->target_arm_torques && (!s->current_arm_dof_pos || !s->current_arm_dof_vel || !hp->arm_coefs)) return DWBC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const DwbcNetCfg& n = *net;
   const float* P = params;
@@ -822,6 +834,8 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
     f.n_leg = n.n_leg; f.n_act = n.n_leg + n.n_arm; f.latent = p.latent; f.rows = rows;
     f.clip = hp->clip_param; f.c_value = hp->value_loss_coef; f.c_ent = hp->entropy_coef; f.c_reg = hp->priv_reg_coef; f.rho = hp->mixing_ratio;
     f.clipped_value = hp->use_clipped_value_loss;
+    f.ts_target = s->target_arm_torques; f.ts_pos = s->current_arm_dof_pos; f.ts_vel = s->current_arm_dof_vel; f.ts_coef = hp->arm_coefs;
+    f.ts_w = hp->torque_supervision_weight;
     TRY(launch_pack2(pl, st));
     TRY(launch_chain2(&A.pr, &C.pr, f, x3, p.queue, st));
     TRY(launch_chain2(&Ab.pr, &Cb.pr, FinArgs{}, x3, p.queue, st));
@@ -839,6 +853,8 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
   a.rows = rows; a.n_leg = n.n_leg; a.n_act = n.n_leg + n.n_arm; a.latent = p.latent;
   a.clip = hp->clip_param; a.c_value = hp->value_loss_coef; a.c_ent = hp->entropy_coef; a.c_reg = hp->priv_reg_coef; a.rho = hp->mixing_ratio;
   a.clipped_value = hp->use_clipped_value_loss;
+  a.ts_target = s->target_arm_torques; a.ts_pos = s->current_arm_dof_pos; a.ts_vel = s->current_arm_dof_vel; a.ts_coef = hp->arm_coefs;
+  a.ts_w = hp->torque_supervision_weight;
   ppo_loss_kernel<<<(rows + 127) / 128, 128, 0, st>>>(a);
   DWBC_LAUNCH_CHECK();
 

@@ -87,6 +87,10 @@ struct FinArgs {
   int n_leg, n_act, latent, rows;
   float clip, c_value, c_ent, c_reg, rho;
   int clipped_value;
+  // arm torque supervision (PPO:224-239, fixed gains PPO:318-323); ts_target == nullptr: off.  Rows of [T*N, n_arm] storage tensors,
+  // ts_coef = [3][n_arm] default p gains, d gains, default dof positions; ts_w = schedule weight (PPO:304-305); losses[4] += mean loss
+  const float* ts_target; const float* ts_pos; const float* ts_vel; const float* ts_coef;
+  float ts_w;
 };
 
 struct C2Launch {
@@ -292,13 +296,22 @@ __device__ __forceinline__ void c2_fin_act(const FinArgs& f, int c, int64_t m, b
   c2_st_group(f.sigma_out + m * f.n_act + off, cnt, vec2, sg);
   f.log_prob[2 * m + c] = lp;
 }
+// Arm torque supervision (PPO:224-239, off in the shipped config WGC:173) of arm joint i: tau = kp (mu + q_default - q) - kd qd (fixed gains,
+// PPO:318-323) on act_inference(obs)[:, -n_arm:] (PPO:230: the arm means this hook holds), loss = w * mean((tau - target)^2) (PPO:236-238).
+// Returns (squared error, d loss / d pre-tanh output).  Deliberately NOT inlined and scalar-only (no array leaves the caller's registers): the
+// optional branch must not cost the hot epilogue anything.
+__device__ __noinline__ float2 c2_fin_torque(const FinArgs& f, int64_t src, int cnt, int i, float mu) {
+  const float kp = f.ts_coef[i];
+  const float e = kp * (mu + f.ts_coef[2 * cnt + i] - f.ts_pos[src * cnt + i]) - f.ts_coef[cnt + i] * f.ts_vel[src * cnt + i] - f.ts_target[src * cnt + i];
+  return make_float2(e * e, 2.0f * f.ts_w / ((float)f.rows * (float)cnt) * e * kp * (1.0f - mu * mu));
+}
 // FIN_PPO (AC:341-345, PPO:199-205): log-prob of the stored action, ratio, mixed advantage, clipped surrogate, entropy and
 // the gradients w.r.t. the mean (through the tanh, AC:157,170) and std of this group
 __device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, bool on, const float* v, int lane) {
   const int off = c == 0 ? 0 : f.n_leg, cnt = c == 0 ? f.n_leg : f.n_act - f.n_leg;
   const bool vec2 = ((f.n_act | f.n_leg) & 1) == 0;
   const float inv2m = 1.0f / (2.0f * (float)f.rows);
-  float l_surr = 0.0f, l_ent = 0.0f, glp = 0.0f;
+  float l_surr = 0.0f, l_ent = 0.0f, glp = 0.0f, l_ts = 0.0f;
   float sg[C2_GRP], act[C2_GRP], gm[C2_GRP];
   c2_ld_group(f.std + off, cnt, vec2, sg);
   if (on) {
@@ -336,6 +349,11 @@ __device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, b
         gm[i] = glp * d / (sg[i] * sg[i]) * (1.0f - v[i] * v[i]);
       }
     }
+    if (c == 1 && f.ts_target != nullptr) {
+#pragma unroll
+      for (int i = 0; i < C2_GRP; ++i)
+        if (i < cnt) { const float2 t = c2_fin_torque(f, src, cnt, i, v[i]); l_ts += t.x; gm[i] += t.y; }
+    }
     float* grow = c == 0 ? f.g_leg + m * f.gleg_ld : f.g_arm + m * f.garm_ld;
     if ((gld & 3) == 0) {
 #pragma unroll
@@ -361,6 +379,10 @@ __device__ __forceinline__ void c2_fin_ppo(const FinArgs& f, int c, int64_t m, b
   }
   const float ss = warp_sum(l_surr * inv2m), se = warp_sum(l_ent * inv2m);
   if (lane == 0) { atomicAdd(f.losses + 0, ss); atomicAdd(f.losses + 1 + 2, se); }
+  if (c == 1 && f.ts_target != nullptr) {          // (warp-uniform)
+    const float st = warp_sum(l_ts / ((float)f.rows * (float)cnt));
+    if (lane == 0) atomicAdd(f.losses + 4, st);
+  }
 }
 // FIN_VALUE (PPO:209-216), channel c
 __device__ __forceinline__ void c2_fin_value(const FinArgs& f, int c, int64_t m, bool on, float val, int lane) {

@@ -59,8 +59,8 @@ class FusedPPO:
                  mixing_schedule=(0.5, 2000, 4000), torque_supervision=False, torque_supervision_schedule=(0.1, 1000, 1000),
                  adaptive_arm_gains=False, min_policy_std=None, dagger_update_freq=20, priv_reg_coef_schedual=(0, 0, 0, 1),
                  world_size=1, process_group=None, precision="tf32x3"):
-        if torque_supervision or adaptive_arm_gains:
-            raise L.DwbcError("torque_supervision / adaptive_arm_gains are disabled for widowGo1 (WGC:168,173) and outside the hot path")
+        if adaptive_arm_gains:
+            raise L.DwbcError("adaptive_arm_gains (a 12-output arm head, AC:111-125,214-215; off for widowGo1, WGC:168) is not implemented")
         if schedule != "fixed":
             raise L.DwbcError("only schedule='fixed' (WGC:352) is implemented")
         self.device = torch.device(device)
@@ -72,7 +72,10 @@ class FusedPPO:
         self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
         self.min_policy_std = None if min_policy_std is None else torch.tensor(min_policy_std, device=self.device, dtype=torch.float).reshape(-1)
         self.mixing_schedule, self.priv_reg_coef_schedual = list(mixing_schedule), list(priv_reg_coef_schedual)
-        self.torque_supervision, self.adaptive_arm_gains = False, False
+        # arm torque supervision with fixed gains (PPO:224-239, 318-323): off in the shipped config (WGC:173), on in PPO's own defaults (PPO:57)
+        self.torque_supervision, self.adaptive_arm_gains = bool(torque_supervision), False
+        self.torque_supervision_schedule = list(torque_supervision_schedule)
+        self._arm_coefs = None
         self.dagger_update_freq = dagger_update_freq
         self.counter = 0
         self.world_size, self.process_group = world_size, process_group
@@ -85,7 +88,7 @@ class FusedPPO:
         hf, hc = ac.hist_range
         self.hist_encoder_optimizer = _AdamState(ac, hf, hc, learning_rate)               # PPO:79
         self.grad = torch.zeros_like(ac.flat)
-        self._losses = torch.zeros(4, device=self.device)
+        self._losses = torch.zeros(5, device=self.device)        # surrogate, value, priv_reg, entropy, arm torques
         self._norm_scratch = torch.zeros(2, dtype=torch.float64, device=self.device)
         self._grad_norm = torch.zeros(1, device=self.device)
         self._ws = None
@@ -104,6 +107,8 @@ class FusedPPO:
         self._act_tmp = [torch.zeros(num_envs, *action_shape, device=self.device) for _ in range(3)] + \
                         [torch.zeros(num_envs, 2, device=self.device) for _ in range(2)]
         self._workspace(max(num_envs, num_envs * num_transitions_per_env // self.num_mini_batches))
+        if self.torque_supervision:
+            self.storage.enable_torque_supervision(self.actor_critic.num_arm_actions)
 
     @property
     def precision(self):
@@ -141,8 +146,24 @@ class FusedPPO:
     def train_mode(self):
         pass
 
-    def set_arm_default_coeffs(self, *a):      # OPR:91; only used by the torque-supervision branch
-        pass
+    def set_arm_default_coeffs(self, default_arm_p_gains, default_arm_d_gains, default_arm_dof_pos):
+        """PPO:307-310 (called at OPR:91).  Kept as one device tensor [3, n_arm] = p gains, d gains, default positions, each broadcast to
+        the arm joints the way PPO:318-323 broadcasts them against the [M, n_arm] batch."""
+        self.default_arm_p_gains, self.default_arm_d_gains, self.default_arm_dof_pos = default_arm_p_gains, default_arm_d_gains, default_arm_dof_pos
+        if not self.torque_supervision:
+            return
+        n_arm = self.actor_critic.num_arm_actions
+        rows = []
+        for x in (default_arm_p_gains, default_arm_d_gains, default_arm_dof_pos):
+            x = torch.as_tensor(x, dtype=torch.float, device=self.device)
+            if x.dim() > 1 and x.shape[0] != 1:
+                raise L.DwbcError("arm coefficients must broadcast to [n_arm] (per-env coefficients are not supported)")
+            rows.append(torch.broadcast_to(x.reshape(-1) if x.dim() else x, (n_arm,)))
+        self._arm_coefs = torch.stack(rows).contiguous()
+
+    def get_torque_supervision_weight(self):
+        sch = self.torque_supervision_schedule
+        return (1 - min(max((self.counter - sch[1]) / sch[2], 0), 1)) * sch[0]                   # PPO:304-305
 
     # ------------------------------------------------------------------ rollout
     def act(self, obs, critic_obs=None, hist_encoding=False, eps=None):
@@ -204,6 +225,10 @@ class FusedPPO:
             L.check(self._lib.dwbc_store_rewards(L.ptr(rewards.float().contiguous(), torch.float32), L.ptr(arm_rewards.float().contiguous(), torch.float32),
                                                  L.ptr(s.values[t]), L.ptr(to8, (torch.uint8, torch.bool)), L.ptr(d8, (torch.uint8, torch.bool)), self.gamma,
                                                  L.ptr(s.rewards[t]), L.ptr(s.dones[t]), s.num_envs, L.stream_ptr()), "dwbc_store_rewards")
+        if self.torque_supervision and isinstance(infos, dict) and "target_arm_torques" in infos:          # PPO:136-142, RS:108-111
+            s.target_arm_torques[t].copy_(infos["target_arm_torques"])
+            s.current_arm_dof_pos[t].copy_(infos["current_arm_dof_pos"])
+            s.current_arm_dof_vel[t].copy_(infos["current_arm_dof_vel"])
         s.step += 1
         self.transition.clear()
 
@@ -234,6 +259,12 @@ class FusedPPO:
         h.use_clipped_value_loss = int(self.use_clipped_value_loss)
         h.max_grad_norm, h.lr, h.beta1, h.beta2, h.adam_eps = self.max_grad_norm, self.learning_rate, 0.9, 0.999, 1e-8
         h.grad_scale = shard.grad_scale(self.world_size)
+        if self.torque_supervision:
+            if self._arm_coefs is None:
+                raise L.DwbcError("torque_supervision needs set_arm_default_coeffs() first (OPR:91)")
+            h.torque_supervision_weight, h.arm_coefs = self.get_torque_supervision_weight(), self._arm_coefs.data_ptr()
+        else:
+            h.torque_supervision_weight, h.arm_coefs = 0.0, None
         return h
 
     def _allreduce(self, first, count):
@@ -285,7 +316,8 @@ class FusedPPO:
         self.counter += 1                                                                 # PPO:259
         self.enforce_min_std()
         self.last_entropy = losses[3]
-        return losses[1], losses[0], 0.0, value_mixing_ratio, 0, losses[2], priv_reg_coef  # PPO:263
+        ts_w = hp.torque_supervision_weight if self.torque_supervision else 0                            # PPO:158
+        return losses[1], losses[0], (losses[4] if self.torque_supervision else 0.0), value_mixing_ratio, ts_w, losses[2], priv_reg_coef  # PPO:263
 
     def update_dagger(self, indices=None):
         """PPO:265-291."""

@@ -53,6 +53,17 @@ class FusedRolloutStorage:
         self._c.advantages, self._c.log_prob = self.advantages.data_ptr(), self.actions_log_prob.data_ptr()
         self._c.hist_latent, self._c.hist_latent_ld = None, 0
         self._hist_latent = None
+        # RS:82-84: the reference always allocates the three torque-supervision tensors; here they exist (and the kernels' branch is on)
+        # only after enable_torque_supervision()
+        self.target_arm_torques = self.current_arm_dof_pos = self.current_arm_dof_vel = None
+
+    def enable_torque_supervision(self, n_arm=6):
+        """RS:82-84 / RS:108-111: [T, N, n_arm] targets of the arm torque-supervision loss (PPO:224-239)."""
+        T, N = self.num_transitions_per_env, self.num_envs
+        self.target_arm_torques, self.current_arm_dof_pos, self.current_arm_dof_vel = (
+            torch.zeros(T, N, n_arm, device=self.device) for _ in range(3))
+        self._c.target_arm_torques, self._c.current_arm_dof_pos = self.target_arm_torques.data_ptr(), self.current_arm_dof_pos.data_ptr()
+        self._c.current_arm_dof_vel = self.current_arm_dof_vel.data_ptr()
 
     def set_hist_latent(self, z):
         """Precomputed history latent of every storage row [T*N, ld] (or None): see DwbcStorage.hist_latent."""

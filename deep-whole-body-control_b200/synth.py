@@ -148,6 +148,16 @@ def rollout_inputs(N: int, T: int, n_obs: int, seed: int) -> dict:
                 time_outs=bernoulli(seed, 305, (T, N), 0.02), eps=normal(seed, 306, (T, N, 18)))
 
 
+def arm_torque_inputs(N: int, T: int, n_arm: int, seed: int) -> dict:
+    """Targets of the arm torque-supervision branch (PPO:136-142, RS:82-84): operational-space torques ~ N(0, 3), arm joint
+    positions ~ U(-1.5, 1.5), velocities ~ N(0, 1); `coefs` = what OPR:91 hands to set_arm_default_coeffs (widow gains WGC:166-167
+    with a per-joint spread so that a swapped coefficient shows, default joint positions ~ U(-0.5, 0.5))."""
+    j = np.arange(n_arm, dtype=np.float32)
+    return dict(target_arm_torques=normal(seed, 311, (T, N, n_arm), 0.0, 3.0), current_arm_dof_pos=uniform(seed, 312, (T, N, n_arm), -1.5, 1.5),
+                current_arm_dof_vel=normal(seed, 313, (T, N, n_arm)),
+                coefs=(np.float32(5.0) + np.float32(0.25) * j, np.float32(0.5) + np.float32(0.05) * j, uniform(seed, 314, (n_arm,), -0.5, 0.5)))
+
+
 def policy_params(shapes, seed: int) -> list:
     """U(-1/sqrt(fan_in), 1/sqrt(fan_in)) per tensor (the bound nn.Linear/Conv1d default init
     uses, `rsl_rl/modules/actor_critic.py` relies on torch defaults); `shapes` = [(name, shape)]."""

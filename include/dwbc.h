@@ -33,7 +33,7 @@ enum {
   DWBC_ERR_LAUNCH = -3       /* cudaGetLastError() != cudaSuccess after the launch */
 };
 
-#define DWBC_ABI_VERSION 2
+#define DWBC_ABI_VERSION 3
 #define DWBC_MAX_DOF 24
 #define DWBC_MAX_TERMS 40   /* active reward terms per channel */
 #define DWBC_MAX_IDX 8      /* penalised / termination contact bodies */
@@ -305,6 +305,11 @@ typedef struct DwbcPpoHyper {
   int32_t use_clipped_value_loss;
   float max_grad_norm, lr, beta1, beta2, adam_eps;
   float grad_scale;              /* 1/world_size applied to the (all-reduced) gradient before the clip */
+  /* arm torque supervision (PPO:224-239, fixed gains PPO:318-323): weight of mean((tau_arm - target)^2) in the loss
+   * (PPO:304-305 schedule, evaluated by the host); 0 or arm_coefs == NULL: branch off.  arm_coefs: device [3][n_arm] =
+   * default arm p gains, d gains, default arm dof positions (PPO:307-310 set_arm_default_coeffs). */
+  float torque_supervision_weight;
+  const float* arm_coefs;
 } DwbcPpoHyper;
 
 /* Rollout storage views (RS:65-84), flattened [T*N, .] */
@@ -315,11 +320,14 @@ typedef struct DwbcStorage {
    * PPO.update never changes the history encoder (its output is detached, PPO:175-176, so those parameters receive no
    * gradient), hence the regulariser target of a row is the same in all epochs.  NULL: computed per mini-batch. */
   const float* hist_latent; int64_t hist_latent_ld;
+  /* optional (torque supervision, RS:82-84,108-111): [T*N, n_arm] each; NULL: branch off */
+  const float* target_arm_torques; const float* current_arm_dof_pos; const float* current_arm_dof_vel;
 } DwbcStorage;
 
 /* One PPO mini-batch, forward + loss + backward (PPO:166-221,244): gathers rows idx[M] from the
  * storage, writes the UNCLIPPED gradient of the mean loss into grad[num_params] (overwritten) and
- * losses_out[4] += (surrogate, value, priv_reg, entropy) means (device accumulators). */
+ * losses_out[5] += (surrogate, value, priv_reg, entropy, arm-torque) means (device accumulators; the last one only
+ * with torque supervision on). */
 int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* params, const DwbcStorage* st, const int64_t* idx,
                             int32_t M, const DwbcPpoHyper* hp, float* grad, float* losses_out, void* workspace,
                             dwbc_stream_t stream);

@@ -207,8 +207,19 @@ def priv_reg_coef(counter, sched):
     return stage * (sched[1] - sched[0]) + sched[0]                                         # PPO:179
 
 
+def torque_supervision_weight(counter, sched):
+    return (1 - min(max((counter - sched[1]) / sched[2], 0), 1)) * sched[0]                 # PPO:304-305
+
+
+def arm_fk_fixed_gains(coefs, target_arm_dof_pos, current_arm_dof_pos, current_arm_dof_vel):
+    """PPO:318-323.  coefs = (default_arm_p_gains, default_arm_d_gains, default_arm_dof_pos) of PPO:307-310."""
+    kp, kd, q0 = coefs
+    return kp * (target_arm_dof_pos + q0 - current_arm_dof_pos) - kd * current_arm_dof_vel
+
+
 def minibatch_loss(P, mb, hp, counter):
-    """Loss of one PPO mini-batch (PPO:166-221).  mb: dict of gathered rows."""
+    """Loss of one PPO mini-batch (PPO:166-239).  mb: dict of gathered rows.  hp["torque_supervision"] (with
+    hp["adaptive_arm_gains"] False) adds the arm torque-supervision term PPO:224-239; hp["arm_coefs"] = the three tensors of PPO:307-310."""
     obs = mb["obs"]
     mean = actor_mean(P, obs, False)
     logp = log_prob2(mean, P["std"], mb["actions"])
@@ -233,15 +244,28 @@ def minibatch_loss(P, mb, hp, counter):
         vloss = (mb["returns"] - value).pow(2).mean()
     creg = priv_reg_coef(counter, hp["priv_reg_coef_schedual"])
     loss = surr + hp["value_loss_coef"] * vloss - hp["entropy_coef"] * ent.mean() + creg * reg
-    return loss, dict(surrogate=surr.detach(), value=vloss.detach(), priv_reg=reg.detach(), priv_reg_coef=creg,
-                      mixing_ratio=rho)
+    info = dict(surrogate=surr.detach(), value=vloss.detach(), priv_reg=reg.detach(), priv_reg_coef=creg, mixing_ratio=rho)
+    if hp.get("torque_supervision", False):
+        assert not hp.get("adaptive_arm_gains", False), "only the fixed-gain branch (PPO:229-231, 318-323) is restated"
+        n_arm = mb["target_arm_torques"].shape[-1]
+        target_arm_dof_pos = actor_mean(P, obs, False)[:, -n_arm:]                          # PPO:230 act_inference(obs)[:, -6:] (same values as `mean`)
+        tau = arm_fk_fixed_gains(hp["arm_coefs"], target_arm_dof_pos, mb["current_arm_dof_pos"], mb["current_arm_dof_vel"])   # PPO:235
+        tloss = (tau - mb["target_arm_torques"]).pow(2).mean()                              # PPO:236
+        w = torque_supervision_weight(counter, hp["torque_supervision_schedule"])           # PPO:237
+        loss = loss + tloss * w                                                             # PPO:238
+        info.update(arm_torques=tloss.detach(), torque_supervision_weight=w)
+    return loss, info
 
 
 def gather(storage, idx):
     f = lambda x: x.flatten(0, 1)[idx]  # noqa: E731                                        RS:165-201
-    return dict(obs=f(storage["observations"]), actions=f(storage["actions"]), values=f(storage["values"]),
-                returns=f(storage["returns"]), old_log_prob=f(storage["actions_log_prob"]),
-                advantages=f(storage["advantages"]))
+    mb = dict(obs=f(storage["observations"]), actions=f(storage["actions"]), values=f(storage["values"]),
+              returns=f(storage["returns"]), old_log_prob=f(storage["actions_log_prob"]),
+              advantages=f(storage["advantages"]))
+    for k in ("target_arm_torques", "current_arm_dof_pos", "current_arm_dof_vel"):           # RS:178-180,199-201
+        if k in storage:
+            mb[k] = f(storage[k])
+    return mb
 
 
 def ppo_update(P, opt: Adam, storage, indices, hp, counter, record=None):

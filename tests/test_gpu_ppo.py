@@ -169,6 +169,53 @@ def test_ppo_update_matches_reference_golden(precision):
     assert alg.counter == counter + 1 and alg.storage.step == 0
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_ppo_update_with_torque_supervision_matches_reference_golden(precision):
+    """PPO:224-239 switched on (fixed-gain arm model PPO:318-323): update() against the unmodified reference's
+    (tests/golden/make_golden_ts.py -> ppo_ts.npz), same stated fp32 tolerances as the branch-off golden.  The arm-torque loss sits in
+    the FIN_PPO epilogue hook of the arm head ('tf32x3') / in ppo_loss_kernel ('fp32'); its targets travel through
+    process_env_step(infos) into the storage rows (PPO:136-142, RS:108-111)."""
+    from test_oracle_golden import ts_hp
+    g, gts = np.load(os.path.join(G, "ppo.npz")), np.load(os.path.join(G, "ppo_ts.npz"))
+    N, T, seed, counter = [int(x) for x in gts["meta"]]
+    ts = synth.arm_torque_inputs(N, T, 6, seed)
+    hp = ts_hp(gts, ts)
+    coefs = hp.pop("arm_coefs")
+    alg = make_alg(N, T, golden_params(g, seed), precision=precision, **hp)
+    alg.set_arm_default_coeffs(*coefs)                                                  # OPR:91
+    alg.counter = counter
+    inp = synth.rollout_inputs(N, T, 860, seed)
+    fill_storage(alg, g, inp, T)
+    s = alg.storage
+    for t in range(T):                                    # the targets arrive the reference's way: infos of process_env_step
+        s.step = t
+        infos = {k: torch.from_numpy(ts[k][t]).cuda() for k in ("target_arm_torques", "current_arm_dof_pos", "current_arm_dof_vel")}
+        infos["time_outs"] = torch.from_numpy(inp["time_outs"][t]).cuda()
+        alg.process_env_step(torch.from_numpy(inp["rew"][t]).cuda(), torch.from_numpy(inp["arm_rew"][t]).cuda(),
+                             torch.from_numpy(inp["dones"][t]).cuda(), infos)
+    np.testing.assert_array_equal(s.target_arm_torques.cpu().numpy(), ts["target_arm_torques"])
+    ac = alg.actor_critic
+    snap = {}
+
+    def on_step(k, when):
+        if k == 0 and when == "step":
+            snap["grad1"], snap["param1"] = alg.grad.clone(), ac.flat.clone()
+
+    res = alg.update(indices=torch.from_numpy(g["perm"]).cuda().long(), on_step=on_step)
+    ref = gts["update_result"]
+    assert abs(res[0] - ref[0]) < 2e-5 * max(1, abs(ref[0])) and abs(res[1] - ref[1]) < 2e-5 and abs(res[5] - ref[5]) < 2e-5
+    assert abs(res[2] - ref[2]) < 1e-4 * abs(ref[2]) and abs(res[4] - ref[4]) < 1e-7 and res[3] == ref[3]
+    g1, p1, p20 = _flat_ref(ac, gts["grad1"]), _flat_ref(ac, gts["param1"]), _flat_ref(ac, gts["param20"])
+    got_g, got_p1, got_p20 = ac.unflat(snap["grad1"]), ac.unflat(snap["param1"]), ac.unflat(ac.flat)
+    for n, _ in ac.manifest:
+        np.testing.assert_allclose(got_g[n].cpu().numpy(), g1[n].numpy(), rtol=1e-3, atol=2e-6, err_msg="grad1 " + n)
+        np.testing.assert_allclose(got_p1[n].cpu().numpy(), p1[n].numpy(), rtol=0, atol=2e-5, err_msg="param1 " + n)
+        np.testing.assert_allclose(got_p20[n].cpu().numpy(), p20[n].numpy(), rtol=0, atol=2e-5, err_msg="param20 " + n)
+    # and the branch is really on: the gradient differs from the branch-off golden
+    off = _flat_ref(ac, g["grad1"])
+    assert max(float((got_g[n].cpu() - off[n]).abs().max()) for n, _ in ac.manifest) > 1e-3
+
+
 def test_dagger_update_matches_reference_golden():
     g = np.load(os.path.join(G, "ppo.npz"))
     N, T, seed, _ = [int(x) for x in g["meta"]]

@@ -36,11 +36,34 @@ def test_schedules_match_reference_formulas():
 def test_unsupported_reference_switches_fail_loudly():
     from dwbc_b200 import _lib as L
     with pytest.raises(L.DwbcError):
-        make_cpu_alg(torque_supervision=True)
-    with pytest.raises(L.DwbcError):
         make_cpu_alg(adaptive_arm_gains=True)
     with pytest.raises(L.DwbcError):
         make_cpu_alg(schedule="adaptive")
+
+
+def test_torque_supervision_host_side():
+    """PPO:304-310, RS:82-84, PPO:136-142 on the host mirror: schedule, coefficient broadcast, storage rows, loud failure without coefficients."""
+    from dwbc_b200 import _lib as L
+    alg = make_cpu_alg(torque_supervision=True, torque_supervision_schedule=[0.1, 1000, 1000])
+    for c in (0, 999, 1000, 1400, 2000, 5000):
+        alg.counter = c
+        assert alg.get_torque_supervision_weight() == PO.torque_supervision_weight(c, [0.1, 1000, 1000])
+    alg.counter = 1400
+    with pytest.raises(L.DwbcError):
+        alg._fill_hp()                                    # OPR:91 has not run
+    alg.set_arm_default_coeffs(torch.arange(6.0) + 5, torch.full((6,), 0.5), torch.zeros(1, 6))
+    assert alg._arm_coefs.shape == (3, 6) and alg._arm_coefs[0].tolist() == [5, 6, 7, 8, 9, 10]
+    hp = alg._fill_hp()
+    assert abs(hp.torque_supervision_weight - 0.06) < 1e-7 and hp.arm_coefs == alg._arm_coefs.data_ptr()
+    with pytest.raises(L.DwbcError):
+        alg.set_arm_default_coeffs(torch.zeros(4, 6), torch.zeros(6), torch.zeros(6))      # per-env coefficients
+    alg.init_storage(4, 3, [860], [None], [18])
+    s = alg.storage
+    assert s.target_arm_torques.shape == s.current_arm_dof_pos.shape == s.current_arm_dof_vel.shape == (3, 4, 6)
+    assert s._c.target_arm_torques == s.target_arm_torques.data_ptr() and s._c.current_arm_dof_vel == s.current_arm_dof_vel.data_ptr()
+    off = make_cpu_alg()
+    off.init_storage(4, 3, [860], [None], [18])
+    assert off.storage.target_arm_torques is None and not off.storage._c.target_arm_torques and off._fill_hp().arm_coefs is None
 
 
 def test_checkpoint_round_trip_keeps_reference_names_and_shapes():

@@ -128,6 +128,46 @@ def test_ppo_oracle_matches_reference_golden():
     assert logs[0]["mixing_ratio"] == res[3] and logs[0]["priv_reg_coef"] == res[6]
 
 
+def ts_storage(g, gts, inp, ts):
+    """Storage dict of the torque-supervision golden: the rollout of ppo.npz + synth.arm_torque_inputs (make_golden_ts.py)."""
+    T = int(gts["meta"][1])
+    f = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    st = dict(observations=torch.from_numpy(inp["obs"])[:T], actions=f("actions"), values=f("values"), returns=f("returns"),
+              actions_log_prob=f("log_prob"), advantages=f("advantages"))
+    st.update({k: torch.from_numpy(ts[k]) for k in ("target_arm_torques", "current_arm_dof_pos", "current_arm_dof_vel")})
+    return st
+
+
+def ts_hp(gts, ts):
+    hp = ppo_hp()
+    hp.update(torque_supervision=True, adaptive_arm_gains=False, torque_supervision_schedule=[float(x) for x in gts["schedule"]],
+              arm_coefs=tuple(torch.from_numpy(np.asarray(c, np.float32)) for c in ts["coefs"]))
+    return hp
+
+
+def test_ppo_oracle_torque_supervision_matches_reference_golden():
+    """PPO:224-239 (fixed-gain arm model PPO:318-323), switched on: the oracle against the unmodified reference's update() (ppo_ts.npz)."""
+    g, gts = np.load(os.path.join(G, "ppo.npz")), np.load(os.path.join(G, "ppo_ts.npz"))
+    N, T, seed, counter = [int(x) for x in gts["meta"]]
+    P = golden_params(g, seed)
+    ts = synth.arm_torque_inputs(N, T, 6, seed)
+    hp = ts_hp(gts, ts)
+    snaps = {}
+
+    def record(k, Pn, Gd, when):
+        if k == 0 and when == "pre_step":
+            snaps["grad1"] = torch.cat([(Gd[n] if Gd[n] is not None else torch.zeros_like(Pn[n])).reshape(-1) for n in Pn])
+
+    logs = PO.ppo_update(P, PO.Adam(list(P.keys()), hp["learning_rate"]), ts_storage(g, gts, synth.rollout_inputs(N, T, 860, seed), ts),
+                         torch.from_numpy(g["perm"]).long(), hp, counter, record)
+    np.testing.assert_allclose(snaps["grad1"].numpy(), gts["grad1"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(torch.cat([P[n].reshape(-1) for n in P]).numpy(), gts["param20"], rtol=0, atol=3e-6)
+    res = gts["update_result"]
+    np.testing.assert_allclose(np.array([float(l["arm_torques"]) for l in logs]), gts["mb_arm_losses"], rtol=1e-6)
+    assert abs(float(np.mean([float(l["arm_torques"]) for l in logs])) - res[2]) < 2e-4 and logs[0]["torque_supervision_weight"] == res[4] == 0.06
+    assert abs(float(torch.stack([l["surrogate"] for l in logs]).mean()) - res[1]) < 1e-5
+
+
 def test_torque_controller_oracle_matches_reference_golden():
     """`_compute_torques` (WG:1262-1295) restatement against the unmodified reference method (tests/golden/make_golden_torques.py)."""
     from dwbc_b200.config import WidowGo1Params
