@@ -989,6 +989,22 @@ extern "C" int dwbc_debug_gemm(int mode, int tc, const float* A, int64_t lda, co
   return rc;
 }
 
+// tuning aid (tools/update_timing.py): time ratio of a one-tile chain item to half a two-tile item in the work-item planner; <= 0 switches
+// the one-tile tail items off
+extern "C" int dwbc_debug_set_chain_single_penalty(double v) {
+  c2_single_penalty = v;
+  return DWBC_OK;
+}
+// tuning aid: deal of the grouped weight-gradient work items (1 = sorted + boustrophedon, 0 = round-robin in construction order)
+extern "C" int dwbc_debug_set_wgrad_snake(int on) {
+  wg_snake = on ? 1 : 0;
+  return DWBC_OK;
+}
+// tuning aid: force the number of one-tile items per program of the large chain launches (-1: planner)
+extern "C" int dwbc_debug_set_chain_singles(int n) {
+  c2_force_singles = n;
+  return DWBC_OK;
+}
 extern "C" int dwbc_debug_set_tc_cycle_buffer(unsigned long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_tc_cycles, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? DWBC_OK : DWBC_ERR_LAUNCH;
 }

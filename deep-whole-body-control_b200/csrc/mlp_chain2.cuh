@@ -24,6 +24,10 @@
 #pragma once
 #include <stdlib.h>
 
+#include <algorithm>
+#include <functional>
+#include <vector>
+
 #include "gemm_tc2.cuh"
 
 namespace dwbc {
@@ -94,7 +98,11 @@ struct FinArgs {
 };
 
 struct C2Launch {
-  int nprog, x3, pair;       // programs (1 or 2), error-compensated mode, tiles per work item (1 or 2)
+  int nprog, x3;             // programs (1 or 2), error-compensated mode
+  // work items of ONE program: np2 two-tile items over the tiles [0, 2 np2), then ns1 one-tile items over the rest.  All two-tile items (of
+  // every program, longest program first) are queued in front of all one-tile items: the tail of a launch is filled with half-size items
+  // (launch_chain2 picks ns1 by simulating the queue on the SM count)
+  int np2, ns1;
   int* queue;                // [2] device counters (next item, finished CTAs), zero between launches
   C2Prog p[2];
   FinArgs fin;
@@ -453,8 +461,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
-  const int pairs = (tiles + L.pair - 1) / L.pair;       // work items per program
-  const int items = pairs * L.nprog;
+  const int n_pair_items = L.np2 * L.nprog;
+  const int items = n_pair_items + L.ns1 * L.nprog;
   const bool x3 = L.x3 != 0;
 
   // running counters, identical in every thread: ops of all items so far (bias slot parity) and ops per slot (phase of that
@@ -470,7 +478,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
     __syncthreads();
     const int item = sh.item;
     if (item >= items) break;
-    const int pi = item / pairs;                         // program 0 (the longer one) first
+    int pi, t0, nslots;                                  // program (0 = the longer one, first), first tile, tiles of this item
+    {
+      const bool two = item < n_pair_items;
+      const int k = two ? item : item - n_pair_items, per = two ? L.np2 : L.ns1;
+      pi = k / per;
+      t0 = two ? 2 * (k - pi * per) : 2 * L.np2 + (k - pi * per);
+      nslots = min(two ? 2 : 1, tiles - t0);
+      asm volatile("" : "+r"(nslots));                   // opaque: one body for both item sizes (the compiler cloned the whole item loop otherwise)
+    }
     // the item's program goes to shared memory: read through the kernel parameter, every field access with a run-time op index is an
     // indexed constant-bank load (LDC c[0x0][R + off]) -- a long-scoreboard stall in front of most addresses and predicates of the epilogue
     if (pi != cur_prog) {
@@ -481,8 +497,6 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
       __syncthreads();
     }
     const C2Prog& pr = sprog;
-    const int t0 = (item - pi * pairs) * L.pair;
-    const int nslots = min(L.pair, tiles - t0);
     const int nops = pr.n_ops;
 
     if (warp == C2_WORKERS) {
@@ -492,9 +506,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
       // tcgen05.mma in an elect / 7 x R2UR.BROADCAST / branch loop: ~300 cycles per MMA, i.e. the MMA thread, not the tensor core or the
       // epilogue, set the pace of the whole kernel.
       const uint32_t b0 = tc_smem_u32(wbuf);
-      // one tile per item (small batches: the rollout's act()): slot Y's tile is unused, so in 3xTF32 mode the low-part image of an op is
-      // fetched into it TOGETHER with the raw image instead of after the first two products (no serial second fetch per op)
-      const bool lo_side = x3 && L.pair == 1;
+      // one tile in this item (small batches: the rollout's act(); the half-size items at the tail of a large launch): slot Y's tile is
+      // unused, so in 3xTF32 mode the low-part image of an op is fetched into it TOGETHER with the raw image instead of after the first
+      // two products (no serial second fetch per op)
+      const bool lo_side = x3 && nslots == 1;
       const uint32_t b0_lo = lo_side ? tc_smem_u32(tile[1]) : b0;
       auto fetch = [&](const float* img, uint32_t wbytes, uint32_t bbytes, uint32_t slot, const float* img_lo = nullptr) {
         if (c2_elect()) {
@@ -914,6 +929,60 @@ struct C2Builder {
 };
 
 // pr1 may be null.  The longer program goes first in the queue.
+// ---- how many tiles of a large launch run as one-tile items ---------------------------------------------------------------------------
+// A launch of T tiles x P programs on S persistent CTAs: with two-tile items only, the last wave is badly quantised (320 tiles x 2 programs on
+// 148 SMs: 12 CTAs get a second long item while 136 wait for a short one, then 24 short items are left for a wave of their own: the
+// makespan is 3.2 short items for 2.4 of work per CTA).  One-tile items are half the work at a worse rate (no second slot to hide the MMA
+// and the weight fetch behind: factor c2_single_penalty, measured), but they fill the tail.  The number of them is chosen by simulating the
+// queue (greedy: a CTA that becomes free takes the next item) with a per-op cost model of the epilogue-bound kernel; the choice depends
+// only on (tiles, programs), so it is cached.
+inline double c2_single_penalty = 1.35;                  // time of a one-tile item / half the time of a two-tile item; <= 0: no one-tile items
+inline double c2_prog_cost(const C2Prog& pr) {
+  double c = 0.0;
+  for (int i = 0; i < pr.n_ops; ++i) c += 0.3 + (double)pr.op[i].npad / 128.0;       // fixed hand-over + epilogue work ~ output chunks
+  return c + 0.3 * pr.n_loads;
+}
+inline double c2_makespan(int tiles, int nprog, const double* cost, int sms, int ns1) {
+  std::vector<double> heap(sms, 0.0);                    // min-heap of the CTAs' free times
+  auto take = [&](double c) {
+    std::pop_heap(heap.begin(), heap.end(), std::greater<double>());
+    heap.back() += c;
+    std::push_heap(heap.begin(), heap.end(), std::greater<double>());
+  };
+  const int np2 = (tiles - ns1 + 1) / 2;
+  const double pen = c2_single_penalty > 0.0 ? c2_single_penalty : 1.35;
+  for (int p = 0; p < nprog; ++p)
+    for (int j = 0; j < np2; ++j) take(2 * j + 1 < tiles - ns1 ? cost[p] : 0.5 * pen * cost[p]);   // (an odd last pair holds one tile)
+  for (int p = 0; p < nprog; ++p)
+    for (int j = 0; j < ns1; ++j) take(0.5 * pen * cost[p]);
+  return *std::max_element(heap.begin(), heap.end());
+}
+inline int c2_force_singles = -1;                         // tuning aid: >= 0 overrides the planner (rounded so that whole pairs stay in front)
+inline int c2_pick_singles(int tiles, int nprog, const double* cost, int sms) {
+  if (c2_force_singles >= 0) {
+    int s1 = c2_force_singles < tiles ? c2_force_singles : tiles;
+    if (s1 > 0 && ((tiles - s1) & 1)) s1 += s1 < tiles ? 1 : -1;
+    return s1;
+  }
+  if (c2_single_penalty <= 0.0) return 0;
+  struct Key { int tiles, nprog, sms; double c0, c1, pen; int ns1; };
+  static thread_local Key cache[8];
+  static thread_local int ncache = 0;
+  for (int i = 0; i < ncache; ++i) {
+    const Key& k = cache[i];
+    if (k.tiles == tiles && k.nprog == nprog && k.sms == sms && k.c0 == cost[0] && k.c1 == cost[1] && k.pen == c2_single_penalty) return k.ns1;
+  }
+  int best = 0;
+  double best_t = c2_makespan(tiles, nprog, cost, sms, 0);
+  for (int s1 = 2 - (tiles & 1); s1 <= tiles && s1 <= 2 * sms; s1 += 2) {      // (tiles - s1) even: whole pairs in front
+    const double t = c2_makespan(tiles, nprog, cost, sms, s1);
+    if (t < best_t * (1.0 - 1e-9)) { best_t = t; best = s1; }
+  }
+  Key& k = cache[ncache < 8 ? ncache++ : 7];
+  k = Key{tiles, nprog, sms, cost[0], cost[1], c2_single_penalty, best};
+  return best;
+}
+
 inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fin, bool x3, int* queue, cudaStream_t st) {
   C2Launch L{};
   L.nprog = pr1 ? 2 : 1;
@@ -938,8 +1007,15 @@ inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fi
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int tiles = (L.p[0].M + TC_M - 1) / TC_M;
-  L.pair = tiles * L.nprog > sms ? 2 : 1;                  // small batches (rollout): one tile per item, spread over more SMs
-  const int items = ((tiles + L.pair - 1) / L.pair) * L.nprog;
+  if (tiles * L.nprog <= sms) {                            // small batches (rollout): one tile per item, spread over more SMs
+    L.np2 = 0;
+    L.ns1 = tiles;
+  } else {
+    double cost[2] = {c2_prog_cost(L.p[0]), L.nprog > 1 ? c2_prog_cost(L.p[1]) : 0.0};
+    L.ns1 = c2_pick_singles(tiles, L.nprog, cost, sms);
+    L.np2 = (tiles - L.ns1 + 1) / 2;
+  }
+  const int items = (L.np2 + L.ns1) * L.nprog;
   const int grid = items < sms ? items : sms;
   const size_t smem = (size_t)C2_SMEM_FLOATS * sizeof(float);
   static bool attr = false;

@@ -10,6 +10,8 @@
 #pragma once
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "gemm_tc2.cuh"
 
 namespace dwbc {
@@ -32,7 +34,10 @@ struct WGItem {
   int Mo, Ni;
   int fastG, fastX;     // 16-byte aligned rows and width % 4 == 0: cp.async path
 };
-struct WGroup { int n, rows, slab, nslab; WGItem it[WG_MAX]; };
+// snake != 0: the GEMMs are sorted by operand width (host) and the work items, enumerated GEMM-major, are dealt to the CTAs boustrophedon
+// (round j forwards for even j, backwards for odd j): every CTA gets the same mix of wide and narrow items.  Dealt round-robin in
+// construction order (snake == 0, the first version) the heaviest CTA carried 1.22 x the mean operand bytes of a widowGo1 mini-batch.
+struct WGroup { int n, rows, slab, nslab, snake; WGItem it[WG_MAX]; };
 
 // elect.sync: true in exactly one lane of the (converged) warp
 __device__ __forceinline__ bool wg_elect() {
@@ -92,7 +97,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
   const uint32_t tmem = sh.tmem_base;
   if (tid == 0) WG_STAMP(62);
   const int items = grp.n * grp.nslab;
-  const int my_items = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int nb = (int)gridDim.x, bid = (int)blockIdx.x;
+  int my_items;
+  if (grp.snake) {
+    const int full = items / nb, rem = items - full * nb;        // the last, partial round runs forwards or backwards like any other
+    my_items = full + ((((full & 1) ? nb - 1 - bid : bid) < rem) ? 1 : 0);
+  } else {
+    my_items = bid < items ? (items - bid + nb - 1) / nb : 0;
+  }
 
   // byte offset of the 16-byte piece (row k, piece c4) inside an operand tile (SWIZZLE_128B_BASE32B, MN-major)
   auto piece_off = [](int k, int c4) -> uint32_t {
@@ -261,9 +273,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
 
   uint32_t cc = 0;                                     // running chunk counter
   for (int j = 0; j < my_items; ++j) {
-    const int w = blockIdx.x + j * gridDim.x;
-    const WGItem& g = grp.it[w % grp.n];
-    const int64_t k_begin = (int64_t)(w / grp.n) * grp.slab;
+    int layer, slab_i;
+    if (grp.snake) {
+      const int e = j * nb + ((j & 1) ? nb - 1 - bid : bid);
+      layer = e / grp.nslab;
+      slab_i = e - layer * grp.nslab;
+    } else {
+      const int w = bid + j * nb;
+      layer = w % grp.n;
+      slab_i = w / grp.n;
+    }
+    const WGItem& g = grp.it[layer];
+    const int64_t k_begin = (int64_t)slab_i * grp.slab;
     const int64_t k_end = min((int64_t)grp.rows, k_begin + grp.slab);
     const int nch = (int)((k_end - k_begin + WCH - 1) / WCH);
     const int Mo = g.Mo, Ni = g.Ni, nipad = (Ni + 15) & ~15;
@@ -388,8 +409,15 @@ struct WGroupBuilder {
   }
 };
 
+inline int wg_snake = 1;                             // tuning aid (dwbc_debug_set_wgrad_snake): 0 = round-robin deal in construction order
+
 inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
   if (g.n <= 0 || rows <= 0) return DWBC_ERR_ARG;
+  g.snake = wg_snake;
+  if (g.snake)         // widest operand pair first (a work item's time goes with the bytes it fetches per row)
+    std::stable_sort(g.it, g.it + g.n, [](const WGItem& a, const WGItem& b) {
+      return ((a.Mo + 15) & ~15) + ((a.Ni + 15) & ~15) > ((b.Mo + 15) & ~15) + ((b.Ni + 15) & ~15);
+    });
   static int sms = 0;
   if (!sms) {
     int dev = 0;

@@ -1,0 +1,33 @@
+/* Profiling / tuning entry points of libdwbc.so.  NOT part of the drop-in boundary (include/dwbc.h): nothing in the product path calls
+ * them; tools/ and tests/test_gpu_gemm.py do.  Declared here so that every exported symbol of the library has a header. */
+#ifndef DWBC_DEBUG_H
+#define DWBC_DEBUG_H
+#include "dwbc.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One GEMM of the selected implementation (tc: 0 = fp32 CUDA cores, 1 = TF32 tcgen05) on plain row-major device matrices.
+ *   mode 0: Y[M,N] = act(X[M,K] W[N,K]^T + b)   mode 1: dX[M,N] = G[M,K] W[K,N]   mode 2: dW[M,N] += G[K,M]^T X[K,N], db += colsum(G) */
+int dwbc_debug_gemm(int mode, int tc, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                    const float* bias, float* dbias, int M, int N, int K, int act, dwbc_stream_t stream);
+
+/* clock64 stamp buffers (device memory, NULL switches the stamps off): tcgen05 GEMM / chain kernels (64 slots per CTA), grouped
+ * weight-gradient kernel, post-physics kernel */
+int dwbc_debug_set_tc_cycle_buffer(unsigned long long* dev_ptr);
+int dwbc_debug_set_wg_cycle_buffer(unsigned long long* dev_ptr);
+int dwbc_debug_set_cycle_buffer(unsigned long long* dev_ptr);
+
+/* Work-item planner of the fused chain kernel (mlp_chain2.cuh): assumed time ratio of a one-tile item to half a two-tile item
+ * (<= 0: no one-tile items at the tail of a large launch), and a forced number of one-tile items per program (-1: planner decides) */
+int dwbc_debug_set_chain_single_penalty(double ratio);
+int dwbc_debug_set_chain_singles(int n);
+
+/* Deal of the grouped weight-gradient work items (wgrad_group.cuh): 1 = GEMMs sorted by operand width, items dealt boustrophedon
+ * (default), 0 = round-robin in construction order */
+int dwbc_debug_set_wgrad_snake(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -27,6 +27,20 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, name), name
 
 
+def test_debug_header_symbols_are_exported(lib):
+    """include/dwbc_debug.h (profiling / tuning hooks, outside the drop-in boundary): every declared symbol exists, and the library
+    exports no dwbc_* symbol that neither header declares."""
+    import subprocess
+    dbg = open(os.path.join(ROOT, "include", "dwbc_debug.h")).read()
+    declared = sorted(set(re.findall(r"\b(dwbc_debug_[a-z_0-9]+)\s*\(", dbg)))
+    assert declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (dwbc_[a-z_0-9]+)$", out, re.M)))
+    assert exported == sorted(L.EXPORTS + declared), set(exported) ^ set(L.EXPORTS + declared)
+
+
 def test_struct_mirrors_match_c_layout(lib):
     sizes = (ctypes.c_int64 * 6)()
     lib.dwbc_struct_sizes(ctypes.byref(sizes))

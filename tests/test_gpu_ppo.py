@@ -280,6 +280,75 @@ def test_minibatch_grad_matches_oracle_autograd_large():
     assert abs(float(ls[2]) - float(info["priv_reg"])) < 1e-4
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32"])
+def test_stock_policy_shape_512_256_128_matches_oracle_autograd(precision):
+    """the stock legged_gym trunk shape (LRC:206-207: actor / critic hidden dims [512, 256, 128]) in front of the
+    widowGo1 heads.  Layers wider than 128 do not fit the fused chain's operand tile, so this configuration runs layer by layer
+    (`gemm_simt_kernel` on 'fp32' / 'tf32x3', `gemm_tc2_kernel` on 'tf32'): rollout forward and the unclipped gradient of one
+    2048-row mini-batch against the oracle (torch autograd on CPU)."""
+    N, T, seed = 256, 8, 33
+    dims = dict(actor_dims=(512, 256, 128), critic_dims=(512, 256, 128))
+    manifest = PO.param_manifest(**dims)
+    vals = synth.policy_params(manifest, seed)
+    P = {n: (torch.tensor([[0.8, 1.0, 1.0] * 4 + [1.0] * 6]) if v is None else torch.from_numpy(v).clone()) for (n, _), v in zip(manifest, vals)}
+    from dwbc_b200.actor_critic import FlatActorCritic
+    from dwbc_b200.ppo import FusedPPO
+    ac = FlatActorCritic(device="cuda:0", num_priv=24, num_hist=10, num_prop=76, actor_hidden_dims=dims["actor_dims"],
+                         critic_hidden_dims=dims["critic_dims"])
+    assert ac.manifest == manifest
+    ac.load_state_dict(P)
+    hp = ppo_hp()
+    alg = FusedPPO(ac, device="cuda:0", **dict(hp, num_mini_batches=1, num_learning_epochs=1, precision=precision))
+    alg.init_storage(N, T, [860], [None], [18])
+    alg.counter = 1500
+    inp = synth.rollout_inputs(N, T, 860, seed)
+    obs = torch.from_numpy(inp["obs"])
+    # rollout forward (PPO.act) on the first step
+    eps = torch.from_numpy(inp["eps"][0])
+    ref_act = PO.policy_act(P, obs[0], eps)
+    alg.act(obs[0].cuda(), obs[0].cuda(), False, eps=eps.cuda())
+    s = alg.storage
+    tol_f = 2e-2 if precision == "tf32" else 2e-5
+    e_mean = float((s.mu[0].cpu() - ref_act["mean"]).abs().max())
+    e_val = float((s.values[0].cpu() - ref_act["values"]).abs().max())
+    assert e_mean < tol_f and e_val < tol_f * max(1.0, float(ref_act["values"].abs().max())), (e_mean, e_val)
+    st = dict(observations=obs[:T], actions=torch.from_numpy(synth.normal(seed, 50, (T, N, 18))),
+              values=torch.from_numpy(synth.normal(seed, 51, (T, N, 2))), returns=torch.from_numpy(synth.normal(seed, 52, (T, N, 2))),
+              actions_log_prob=torch.from_numpy(synth.normal(seed, 53, (T, N, 2), -20.0, 1.0)),
+              advantages=torch.from_numpy(synth.normal(seed, 54, (T, N, 2))))
+    s._obs_all.copy_(obs.cuda())
+    for k in ("actions", "values", "returns", "actions_log_prob", "advantages"):
+        getattr(s, k).copy_(st[k].cuda())
+    idx = torch.from_numpy(np.argsort(synth.uniform(seed, 60, (N * T,)))).long()
+    for n in P:
+        P[n].requires_grad_(True)
+    loss, info = PO.minibatch_loss(P, PO.gather(st, idx), hp, 1500)
+    loss.backward()
+    import ctypes as C
+    from dwbc_b200 import _lib as L
+    h = alg._fill_hp()
+    alg._set_precision()
+    alg._losses.zero_()
+    L.check(L.lib().dwbc_ppo_minibatch_grad(C.addressof(ac.net_cfg), L.ptr(ac.flat), s.c_struct_ptr(), L.ptr(idx.cuda()), N * T,
+                                            C.addressof(h), L.ptr(alg.grad), L.ptr(alg._losses), L.ptr(alg._workspace(N * T)),
+                                            L.stream_ptr()), "grad")
+    got = ac.unflat(alg.grad)
+    worst = 0.0
+    tol_g = 5e-2 if precision == "tf32" else 2e-3
+    for n in P:
+        ref = P[n].grad if P[n].grad is not None else torch.zeros_like(P[n])
+        scale = max(float(ref.abs().max()), 1e-6)
+        err = float((got[n].cpu() - ref).abs().max()) / scale
+        worst = max(worst, err)
+        assert err < tol_g, (n, err)
+    ls = alg._losses.cpu()
+    print(f"[{precision}] 512/256/128 trunks: act mean err {e_mean:.3g}, value err {e_val:.3g}, worst per-tensor gradient error / scale {worst:.3g}")
+    rel = 2e-2 if precision == "tf32" else 1e-4
+    assert abs(float(ls[0]) - float(info["surrogate"])) < rel * max(1.0, abs(float(info["surrogate"])))
+    assert abs(float(ls[1]) - float(info["value"])) < rel * max(1.0, abs(float(info["value"])))
+    assert abs(float(ls[2]) - float(info["priv_reg"])) < rel
+
+
 # Tolerances of the plain TF32 path = 2 x the errors MEASURED on B200 against the reference golden vectors (printed by the test;
 # operands truncated to 10 mantissa bits by the tensor core, fp32 accumulation, up to 6 layers deep).  The bound on the parameters is on
 # the RMS, not the max: Adam's update is ~lr * sign(g) for small |g|, so one entry whose tiny gradient changes sign moves by up to 2*lr
@@ -365,11 +434,29 @@ def test_fused_chain_forward_matches_fp32_path_many_tiles(hist, precision):
     assert all(torch.isfinite(t).all() for t in out[precision])
 
 
+@pytest.mark.parametrize("singles,snake", [(-1, 1), (0, 0), (37, 1), (-1, 0)])
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
-def test_fused_chain_backward_matches_fp32_path_many_tiles(precision):
+def test_fused_chain_backward_matches_fp32_path_many_tiles(precision, singles, snake):
     """Mini-batch gradient through the fused forward chains (loss in the epilogue), backward chains and the MN-major weight-gradient GEMMs
     against the exact-fp32 layer-wise path of the same library, at a row count that gives every CTA several tile pairs plus a ragged one.
-    Tolerances: CHAIN_TOL, per parameter tensor ||g - g_fp32|| <= tol ||g_fp32|| (+ 1e-7 abs)."""
+    Tolerances: CHAIN_TOL, per parameter tensor ||g - g_fp32|| <= tol ||g_fp32|| (+ 1e-7 abs).
+    `singles`: one-tile work items per program at the tail of the chain launches (-1: the planner of launch_chain2 decides, 0: two-tile
+    items only -- the odd last pair then holds one tile --, 37: forced, the ragged last tile runs as a one-tile item); `snake`: deal of
+    the grouped weight-gradient work items (1: sorted by operand width, boustrophedon; 0: round-robin in construction order)."""
+    import ctypes as C
+    from dwbc_b200 import _lib as L
+    L.lib().dwbc_debug_set_chain_singles.argtypes = [C.c_int]
+    L.lib().dwbc_debug_set_wgrad_snake.argtypes = [C.c_int]
+    L.lib().dwbc_debug_set_chain_singles(singles)
+    L.lib().dwbc_debug_set_wgrad_snake(snake)
+    try:
+        _chain_backward_many_tiles(precision)
+    finally:
+        L.lib().dwbc_debug_set_chain_singles(-1)
+        L.lib().dwbc_debug_set_wgrad_snake(1)
+
+
+def _chain_backward_many_tiles(precision):
     import ctypes as C
     from dwbc_b200 import _lib as L
     g = np.load(os.path.join(G, "ppo.npz"))
