@@ -1000,6 +1000,11 @@ extern "C" int dwbc_debug_set_wgrad_snake(int on) {
   wg_snake = on ? 1 : 0;
   return DWBC_OK;
 }
+extern "C" int dwbc_debug_set_wgrad_items(int per_cta) {
+  if (per_cta < 1 || per_cta > 64) return DWBC_ERR_ARG;
+  wg_items_per_cta = per_cta;
+  return DWBC_OK;
+}
 // tuning aid: force the number of one-tile items per program of the large chain launches (-1: planner)
 extern "C" int dwbc_debug_set_chain_singles(int n) {
   c2_force_singles = n;

@@ -409,6 +409,7 @@ struct WGroupBuilder {
   }
 };
 
+inline int wg_items_per_cta = 4;                     // tuning aid (dwbc_debug_set_wgrad_items)
 inline int wg_snake = 1;                             // tuning aid (dwbc_debug_set_wgrad_snake): 0 = round-robin deal in construction order
 
 inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
@@ -426,7 +427,7 @@ inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
   }
   g.rows = rows;
   // slab length: ~4 work items per CTA, at least 4 chunks so that the epilogue stays amortised
-  constexpr int per_cta = 4;                           // work items per CTA
+  const int per_cta = wg_items_per_cta;                // work items per CTA
   int64_t total_items = (int64_t)per_cta * sms;
   int64_t nslab = (total_items + g.n - 1) / g.n;
   int64_t slab = (rows + nslab - 1) / nslab;

@@ -26,6 +26,8 @@ int dwbc_debug_set_chain_singles(int n);
 /* Deal of the grouped weight-gradient work items (wgrad_group.cuh): 1 = GEMMs sorted by operand width, items dealt boustrophedon
  * (default), 0 = round-robin in construction order */
 int dwbc_debug_set_wgrad_snake(int on);
+/* work items per CTA the slab length of the grouped weight-gradient launch aims at (default 4) */
+int dwbc_debug_set_wgrad_items(int per_cta);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ lib = L.lib()
 lib.dwbc_debug_set_chain_singles.argtypes = [C.c_int]
 lib.dwbc_debug_set_chain_single_penalty.argtypes = [C.c_double]
 lib.dwbc_debug_set_wgrad_snake.argtypes = [C.c_int]
+lib.dwbc_debug_set_wgrad_items.argtypes = [C.c_int]
 for prec in (sys.argv[1:] or ["tf32x3", "tf32"]):
     ac = FlatActorCritic(device="cuda:0", seed=0, init_std=[[0.8, 1.0, 1.0] * 4 + [1.0] * 6], num_priv=24, num_hist=10, num_prop=76)
     alg = FusedPPO(ac, device="cuda:0", precision=prec, num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95,
@@ -19,14 +20,16 @@ for prec in (sys.argv[1:] or ["tf32x3", "tf32"]):
     alg.init_storage(N, T, [860], [None], [18]); alg.counter = 1500
     s = alg.storage
     s._obs_all.normal_(); s.actions.normal_(); s.values.normal_(); s.returns.normal_(); s.advantages.normal_(); s.actions_log_prob.normal_().sub_(20)
-    for singles, pen, snake in ((0, 1.35, 0), (0, 1.35, 1), (24, 1.35, 1), (48, 1.35, 1), (72, 1.35, 1), (96, 1.35, 1), (120, 1.35, 1), (160, 1.35, 1),
-                                (-1, 1.2, 1), (-1, 1.35, 1), (-1, 1.6, 1), (0, 1.35, 0), (0, 1.35, 1)):
+    for singles, pen, snake, wgi in ((0, 1.35, 0, 4), (0, 1.35, 1, 4), (0, 1.35, 1, 2), (0, 1.35, 1, 3), (0, 1.35, 1, 6), (0, 1.35, 1, 8),
+                                     (24, 1.35, 1, 4), (48, 1.35, 1, 4), (72, 1.35, 1, 4), (96, 1.35, 1, 4), (120, 1.35, 1, 4), (160, 1.35, 1, 4),
+                                     (-1, 1.2, 1, 4), (-1, 1.35, 1, 4), (-1, 1.6, 1, 4), (0, 1.35, 0, 4), (0, 1.35, 1, 4)):
         lib.dwbc_debug_set_chain_singles(singles); lib.dwbc_debug_set_chain_single_penalty(pen); lib.dwbc_debug_set_wgrad_snake(snake)
+        lib.dwbc_debug_set_wgrad_items(wgi)
         alg.update(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(4):
             alg.update()
         e1.record(); torch.cuda.synchronize()
-        print(json.dumps({"precision": prec, "singles_per_program": singles, "penalty": pen, "wgrad_snake": snake, "update_ms": round(e0.elapsed_time(e1) / 4, 3)}), flush=True)
-    lib.dwbc_debug_set_chain_singles(-1); lib.dwbc_debug_set_chain_single_penalty(1.35); lib.dwbc_debug_set_wgrad_snake(1)
+        print(json.dumps({"precision": prec, "singles_per_program": singles, "penalty": pen, "wgrad_snake": snake, "wgrad_items_per_cta": wgi, "update_ms": round(e0.elapsed_time(e1) / 4, 3)}), flush=True)
+    lib.dwbc_debug_set_chain_singles(-1); lib.dwbc_debug_set_chain_single_penalty(1.35); lib.dwbc_debug_set_wgrad_snake(1); lib.dwbc_debug_set_wgrad_items(4)
