@@ -34,9 +34,12 @@ struct WGItem {
   int Mo, Ni;
   int fastG, fastX;     // 16-byte aligned rows and width % 4 == 0: cp.async path
 };
-// snake != 0: the GEMMs are sorted by operand width (host) and the work items, enumerated GEMM-major, are dealt to the CTAs boustrophedon
-// (round j forwards for even j, backwards for odd j): every CTA gets the same mix of wide and narrow items.  Dealt round-robin in
-// construction order (snake == 0, the first version) the heaviest CTA carried 1.22 x the mean operand bytes of a widowGo1 mini-batch.
+// snake != 0 (experiment, OFF by default): the GEMMs are sorted by operand width (host) and the work items, enumerated GEMM-major, are
+// dealt to the CTAs boustrophedon (round j forwards for even j, backwards for odd j), so that every CTA gets the same mix of wide and
+// narrow items -- dealt round-robin in construction order (snake == 0) the heaviest CTA carries 1.22 x the mean operand bytes of a
+// widowGo1 mini-batch.  MEASURED SLOWER on B200 (update() 21.83 against 21.12 ms, 3xTF32; 17.36 against 16.92 ms, TF32): GEMM-major
+// order makes all 148 CTAs reduce into the SAME 64 KB dW at the same time (red.global.add contention in L2), round-robin spreads the
+// epilogues of one moment over all 17 GEMMs.
 struct WGroup { int n, rows, slab, nslab, snake; WGItem it[WG_MAX]; };
 
 // elect.sync: true in exactly one lane of the (converged) warp
@@ -410,7 +413,7 @@ struct WGroupBuilder {
 };
 
 inline int wg_items_per_cta = 4;                     // tuning aid (dwbc_debug_set_wgrad_items)
-inline int wg_snake = 1;                             // tuning aid (dwbc_debug_set_wgrad_snake): 0 = round-robin deal in construction order
+inline int wg_snake = 0;                             // tuning aid (dwbc_debug_set_wgrad_snake): 0 = round-robin deal in construction order
 
 inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
   if (g.n <= 0 || rows <= 0) return DWBC_ERR_ARG;

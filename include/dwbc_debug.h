@@ -23,8 +23,8 @@ int dwbc_debug_set_cycle_buffer(unsigned long long* dev_ptr);
 int dwbc_debug_set_chain_single_penalty(double ratio);
 int dwbc_debug_set_chain_singles(int n);
 
-/* Deal of the grouped weight-gradient work items (wgrad_group.cuh): 1 = GEMMs sorted by operand width, items dealt boustrophedon
- * (default), 0 = round-robin in construction order */
+/* Deal of the grouped weight-gradient work items (wgrad_group.cuh): 0 = round-robin in construction order (default), 1 = GEMMs
+ * sorted by operand width, items dealt boustrophedon (measured slower: all CTAs reduce into the same dW at the same time) */
 int dwbc_debug_set_wgrad_snake(int on);
 /* work items per CTA the slab length of the grouped weight-gradient launch aims at (default 4) */
 int dwbc_debug_set_wgrad_items(int per_cta);

@@ -396,7 +396,9 @@ def test_tf32_tensor_core_path_matches_reference_within_stated_tolerance():
 
 
 # forward: max abs difference of means / values to the exact-fp32 path; gradient: ||dg|| / ||g|| per parameter tensor
-CHAIN_TOL = {"tf32": dict(fwd=8e-3, grad=1e-2, loss=2e-3), "tf32x3": dict(fwd=2e-5, grad=2e-5, loss=2e-5)}
+# (loss: the reported means are fp32 atomic sums over ~38 k rows; their accumulation order changes with the work-item plan and from run to
+# run -- 0.7e-5 ... 2.2e-5 relative seen on B200 for the SAME gradients --, so the 3xTF32 bound is 3 x the largest value seen)
+CHAIN_TOL = {"tf32": dict(fwd=8e-3, grad=1e-2, loss=2e-3), "tf32x3": dict(fwd=2e-5, grad=2e-5, loss=6e-5)}
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
@@ -453,7 +455,7 @@ def test_fused_chain_backward_matches_fp32_path_many_tiles(precision, singles, s
         _chain_backward_many_tiles(precision)
     finally:
         L.lib().dwbc_debug_set_chain_singles(-1)
-        L.lib().dwbc_debug_set_wgrad_snake(1)
+        L.lib().dwbc_debug_set_wgrad_snake(0)
 
 
 def _chain_backward_many_tiles(precision):

@@ -20,9 +20,8 @@ for prec in (sys.argv[1:] or ["tf32x3", "tf32"]):
     alg.init_storage(N, T, [860], [None], [18]); alg.counter = 1500
     s = alg.storage
     s._obs_all.normal_(); s.actions.normal_(); s.values.normal_(); s.returns.normal_(); s.advantages.normal_(); s.actions_log_prob.normal_().sub_(20)
-    for singles, pen, snake, wgi in ((0, 1.35, 0, 4), (0, 1.35, 1, 4), (0, 1.35, 1, 2), (0, 1.35, 1, 3), (0, 1.35, 1, 6), (0, 1.35, 1, 8),
-                                     (24, 1.35, 1, 4), (48, 1.35, 1, 4), (72, 1.35, 1, 4), (96, 1.35, 1, 4), (120, 1.35, 1, 4), (160, 1.35, 1, 4),
-                                     (-1, 1.2, 1, 4), (-1, 1.35, 1, 4), (-1, 1.6, 1, 4), (0, 1.35, 0, 4), (0, 1.35, 1, 4)):
+    for singles, pen, snake, wgi in ((0, 1.35, 0, 4), (-1, 1.35, 0, 4), (-1, 1.35, 0, 3), (-1, 1.35, 0, 5), (-1, 1.35, 0, 6), (-1, 1.35, 0, 8), (-1, 1.35, 0, 12),
+                                     (200, 1.35, 0, 4), (320, 1.35, 0, 4), (-1, 1.35, 0, 4), (0, 1.35, 0, 4)):
         lib.dwbc_debug_set_chain_singles(singles); lib.dwbc_debug_set_chain_single_penalty(pen); lib.dwbc_debug_set_wgrad_snake(snake)
         lib.dwbc_debug_set_wgrad_items(wgi)
         alg.update(); torch.cuda.synchronize()
@@ -32,4 +31,4 @@ for prec in (sys.argv[1:] or ["tf32x3", "tf32"]):
             alg.update()
         e1.record(); torch.cuda.synchronize()
         print(json.dumps({"precision": prec, "singles_per_program": singles, "penalty": pen, "wgrad_snake": snake, "wgrad_items_per_cta": wgi, "update_ms": round(e0.elapsed_time(e1) / 4, 3)}), flush=True)
-    lib.dwbc_debug_set_chain_singles(-1); lib.dwbc_debug_set_chain_single_penalty(1.35); lib.dwbc_debug_set_wgrad_snake(1); lib.dwbc_debug_set_wgrad_items(4)
+    lib.dwbc_debug_set_chain_singles(-1); lib.dwbc_debug_set_chain_single_penalty(1.35); lib.dwbc_debug_set_wgrad_snake(0); lib.dwbc_debug_set_wgrad_items(4)

@@ -8,6 +8,7 @@ timeout -k 10 700 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpur
 echo "pytest rc=$?" >> gpurun_out/gputest.log
 timeout -k 10 240 python tools/chain_split_sweep.py tf32x3 tf32 > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err
 echo "sweep rc=$?" >> gpurun_out/sweep.err
+timeout -k 10 200 python tools/chain_profile.py update tf32x3 > gpurun_out/chain_stamps_x3.txt 2>&1
 timeout -k 10 500 python bench.py > gpurun_out/bench_flat.json 2> gpurun_out/bench_flat.err
 echo "bench rc=$?" >> gpurun_out/bench_flat.err
 tail -5 gpurun_out/gputest.log; cat gpurun_out/sweep.jsonl; tail -c 1500 gpurun_out/bench_flat.json
