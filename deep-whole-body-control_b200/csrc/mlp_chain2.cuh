@@ -225,19 +225,47 @@ __device__ __forceinline__ void c2_warp_arrive(uint64_t* bar, int lane) {
 
 constexpr float C2_LOG_SQRT_2PI = 0.91893853320467274178f;
 
+// ---- packed fp32 pairs ---------------------------------------------------------------------------------------------------
+// sm_100 issues add / sub / mul / fma on TWO fp32 values per lane as one instruction (PTX .f32x2 on a 64-bit register -> FADD2 / FMUL2 /
+// FFMA2).  The epilogues are bound by their instruction stream (ncu: 30 warp instructions per output element, 0.16 IPC per scheduler with two
+// worker warps each, tensor pipe 12 % active), so the element-wise fp32 arithmetic runs on pairs; max / min / ex2 / and have no paired form.
+// Packing two registers that tcgen05.ld, a 16-byte load or an earlier paired instruction delivered side by side costs no instruction.
+__device__ __forceinline__ uint64_t c2_pk(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void c2_upk(uint64_t p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ uint64_t c2_add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t c2_sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t c2_mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// 2^x, flush-to-zero form: ONE MUFU.EX2.  (__expf = ex2.approx.f32 of x * log2 e WITHOUT .ftz, which ptxas wraps in a range test and two
+// scaling multiplies per element for results in the denormal range -- irrelevant for e^x - 1.)
+__device__ __forceinline__ float c2_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+constexpr float C2_LOG2E = 1.4426950408889634f;
+// low parts x - trunc_tf32(x) of a pair
+__device__ __forceinline__ uint64_t c2_lo2(uint64_t p) { return c2_sub2(p, p & 0xFFFFE000FFFFE000ull); }
+// low parts of a 32-column chunk, in place
+__device__ __forceinline__ void c2_lo_chunk(float* v) {
+#pragma unroll
+  for (int jj = 0; jj < 32; jj += 2) c2_upk(c2_lo2(c2_pk(v[jj], v[jj + 1])), v[jj], v[jj + 1]);
+}
+
 template <int kAct, bool kFull>
 __device__ __forceinline__ void c2_bias_act(float* v, const float* bias, int nvalid) {
+  const uint64_t l2e = c2_pk(C2_LOG2E, C2_LOG2E), m1 = c2_pk(-1.0f, -1.0f);
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * j4);
-    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int jj = 4 * j4 + e;
-      float x = v[jj] + bb[e];
-      if (kAct == ACT_ELU) x = fmaxf(x, 0.0f) + (__expf(fminf(x, 0.0f)) - 1.0f);      // ELU without a select: max(x,0) + (e^{min(x,0)} - 1)
-      if (kAct == ACT_TANH) x = t2_tanh(x);
-      v[jj] = (kFull || jj < nvalid) ? x : 0.0f;
+    for (int h = 0; h < 2; ++h) {
+      const int jj = 4 * j4 + 2 * h;
+      float x0, x1;
+      c2_upk(c2_add2(c2_pk(v[jj], v[jj + 1]), h ? c2_pk(b4.z, b4.w) : c2_pk(b4.x, b4.y)), x0, x1);
+      if (kAct == ACT_ELU) {        // ELU without a select: max(x,0) + (e^{min(x,0)} - 1); 5 instructions per element (9 as scalar code with __expf)
+        float e0, e1;
+        c2_upk(c2_mul2(c2_pk(fminf(x0, 0.0f), fminf(x1, 0.0f)), l2e), e0, e1);
+        c2_upk(c2_add2(c2_add2(c2_pk(c2_ex2(e0), c2_ex2(e1)), m1), c2_pk(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), x0, x1);
+      }
+      if (kAct == ACT_TANH) { x0 = t2_tanh(x0); x1 = t2_tanh(x1); }
+      v[jj] = (kFull || jj < nvalid) ? x0 : 0.0f;
+      v[jj + 1] = (kFull || jj + 1 < nvalid) ? x1 : 0.0f;
     }
   }
 }
@@ -639,7 +667,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 t = *reinterpret_cast<const float4*>(trow + (size_t)(ci * 8 + j4) * 32);
-            v[4 * j4] = tf32_lo(t.x); v[4 * j4 + 1] = tf32_lo(t.y); v[4 * j4 + 2] = tf32_lo(t.z); v[4 * j4 + 3] = tf32_lo(t.w);
+            c2_upk(c2_lo2(c2_pk(t.x, t.y)), v[4 * j4], v[4 * j4 + 1]);
+            c2_upk(c2_lo2(c2_pk(t.z, t.w)), v[4 * j4 + 2], v[4 * j4 + 3]);
           }
           c2_st32(tmem + s * 256 + 128 + ((uint32_t)(q * 32) << 16) + ci * 32, v);
         }
@@ -743,20 +772,29 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
                 for (int j4 = 0; j4 < 8; ++j4) {
                   if (c0 + 4 * j4 < o.N) {
                     const float4 t = *reinterpret_cast<const float4*>(ar + 4 * j4);
-                    v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+                    c2_upk(c2_add2(c2_pk(v[4 * j4], v[4 * j4 + 1]), c2_pk(t.x, t.y)), v[4 * j4], v[4 * j4 + 1]);
+                    c2_upk(c2_add2(c2_pk(v[4 * j4 + 2], v[4 * j4 + 3]), c2_pk(t.z, t.w)), v[4 * j4 + 2], v[4 * j4 + 3]);
                   }
                 }
               }
-              if (use_x) {
+              if (use_x) {                                   // AC ELU / tanh derivatives from the layer's OUTPUTS
+                if (o.act == ACT_TANH) {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                  const float xx = x[u][jj];
-                  const float d = o.act == ACT_TANH ? 1.0f - xx * xx : (xx > 0.0f ? 1.0f : xx + 1.0f);   // AC ELU / tanh derivatives from the outputs
-                  v[jj] *= d;
+                  for (int jj = 0; jj < 32; ++jj) v[jj] *= 1.0f - x[u][jj] * x[u][jj];
+                } else {                                     // ELU'(y) = y > 0 ? 1 : y + 1 = min(y + 1, 1), on pairs
+                  const uint64_t one2 = c2_pk(1.0f, 1.0f);
+#pragma unroll
+                  for (int jj = 0; jj < 32; jj += 2) {
+                    float d0, d1;
+                    c2_upk(c2_add2(c2_pk(x[u][jj], x[u][jj + 1]), one2), d0, d1);
+                    c2_upk(c2_mul2(c2_pk(v[jj], v[jj + 1]), c2_pk(fminf(d0, 1.0f), fminf(d1, 1.0f))), v[jj], v[jj + 1]);
+                  }
                 }
               }
+              if (o.N - c0 < 32) {                           // ragged last chunk: the pad columns are operand columns of the next op
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) v[jj] = c0 + jj < o.N ? v[jj] : 0.0f;
+                for (int jj = 0; jj < 32; ++jj) v[jj] = c0 + jj < o.N ? v[jj] : 0.0f;
+              }
             }
             if (o.out_col0 >= 0) {
               float* otile = tile[s] + ((size_t)((r >> 3) * 32 + ((o.out_col0 + c0) >> 2)) * 8 + (r & 7)) * 4;
@@ -783,8 +821,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
               }
             }
             if (x3 && o.out_col0 >= 0) {                       // low parts last, in place: v is dead afterwards
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) v[jj] = tf32_lo(v[jj]);
+              c2_lo_chunk(v);
               c2_st32(tmem + s * 256 + 128 + ((uint32_t)(q * 32) << 16) + o.out_col0 + c0, v);
             }
           }
