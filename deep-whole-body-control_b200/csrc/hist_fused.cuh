@@ -54,16 +54,20 @@ __global__ void __launch_bounds__(HF_THREADS) hist_fused_kernel(const HistFusedA
   for (int o = 0; o < 20; ++o) { c1a[o] = 0.0f; c1b[o] = w[HF_B1 + o]; c1prev[o] = 0.0f; }
 #pragma unroll
   for (int o = 0; o < 32; ++o) z[o] = w[HF_BL + o];
+  float4 xnext = __ldg(reinterpret_cast<const float4*>(hp));
 #pragma unroll 1
   for (int t = 0; t < 10; ++t) {
     // ---- projection of step t: h = ELU(Wp x + bp) ----
     float h[32];
 #pragma unroll
     for (int o = 0; o < 32; ++o) h[o] = w[HF_BP + o];
+    // (the whole [10][76] block of a row is contiguous: the next 16 bytes -- of this step or the first of the next one -- are requested
+    // before the 128 FMAs of the current four inputs, so a thread always has one load in flight instead of waiting for each in turn)
     const float4* x4p = reinterpret_cast<const float4*>(hp + t * 76);
 #pragma unroll 1
     for (int i4 = 0; i4 < 19; ++i4) {
-      const float4 x4 = __ldg(x4p + i4);
+      const float4 x4 = xnext;
+      if (t * 19 + i4 + 1 < 190) xnext = __ldg(x4p + i4 + 1);
       const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {

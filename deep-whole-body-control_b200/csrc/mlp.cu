@@ -340,56 +340,80 @@ static void chain_head(C2Builder& b, const float* P, const float* trunk, int tru
 
 // Programs of the forward pass.  z_hist == nullptr: latent from the privileged encoder (computed inside the chain); else the history
 // latent [rows, zld].  `loss`: update mode (hooks FIN_REG / FIN_PPO / FIN_VALUE), else rollout mode (FIN_ACT), else none (fin_mode 0).
+// With A2 / C2 (inference only: `store` off) the two heads of a network become TWO programs that each recompute the short common part
+// (encoder + backbone): a 4096-row rollout then is 4 programs x 32 tiles = 128 one-tile items of at most 6 ops on 128 SMs instead of
+// 2 x 32 items of 9 / 7 ops on 64 SMs -- the launch is as long as its longest item.
 static int build_forward(const DwbcNetCfg& n, const float* P, const float* obs, const int64_t* idx, int64_t obs_stride, const float* z_hist, int zld,
-                         const Plan& p, float* value, bool store, int fin_mode, C2Builder* A, C2Builder* C) {
+                         const Plan& p, float* value, bool store, int fin_mode, C2Builder* A, C2Builder* C, C2Builder* A2 = nullptr,
+                         C2Builder* C2 = nullptr) {
   const int Lld = (int)align_up(p.latent, 4);
+  if ((A2 || C2) && store) return DWBC_ERR_ARG;
   if (A) {
     const int in0 = n.num_prop + p.latent;
-    int first_main = 0;
-    if (z_hist) {
-      A->load(rowmat(z_hist, zld), p.latent, 0, 32, 0);
-    } else {
-      A->load(rowmat_gather(obs + n.num_prop, idx, obs_stride), n.num_priv, C2_COL_PRIV, C2_COL_PRIV + pad8(n.num_priv), 0);
-      A->fwd(P + n.off_priv_w[0], n.num_priv, P + n.off_priv_b[0], n.priv_dims[0], ACT_ELU, C2_COL_PRIV, pad8(n.num_priv), 1,      // AC:219-221
-             C2PackSeg{0, 0, n.num_priv}, C2PackSeg{0, 0, 0}, C2_COL_HID, store ? p.priv[0] : nullptr, align_up(n.priv_dims[0], 4));
-      A->fwd(P + n.off_priv_w[1], n.priv_dims[0], P + n.off_priv_b[1], p.latent, ACT_ELU, C2_COL_HID, pad8(n.priv_dims[0]), 1,
-             C2PackSeg{0, 0, n.priv_dims[0]}, C2PackSeg{0, 0, 0}, 0, store ? p.priv[1] : nullptr, Lld, fin_mode == 2 ? FIN_REG : FIN_NONE, 0);
-      first_main = 2;
-    }
-    const int k0 = pad8(C2_COL_PROP + n.num_prop);
-    A->load(rowmat_gather(obs, idx, obs_stride), n.num_prop, C2_COL_PROP, k0, first_main);
-    // backbone layer 0 over cat([obs_prop, z]) (AC:211): z occupies tile columns [0, latent), obs_prop [32, 32 + num_prop)
     const int na = n.n_actor_layers;
-    A->fwd(P + n.off_actor_w[0], in0, P + n.off_actor_b[0], n.actor_dims[0], ACT_ELU, 0, k0, 2, C2PackSeg{0, n.num_prop, p.latent},
-           C2PackSeg{C2_COL_PROP, 0, n.num_prop}, 0, (store || na == 1) ? p.ab[0] : nullptr, n.actor_dims[0], FIN_NONE, 0, img_dim(n.actor_dims[0]) && (store || na == 1));
-    int in = n.actor_dims[0];
-    for (int l = 1; l < na; ++l) {                                                   // AC:211-213
-      A->fwd(P + n.off_actor_w[l], in, P + n.off_actor_b[l], n.actor_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
-             (store || l == na - 1) ? p.ab[l] : nullptr, n.actor_dims[l], FIN_NONE, 0, img_dim(n.actor_dims[l]) && (store || l == na - 1));
-      in = n.actor_dims[l];
-    }
+    // encoder (or the history latent) + backbone; returns the backbone's width.  `keep`: the last backbone layer is stored for a second head
+    auto common = [&](C2Builder& B, bool keep) {
+      int first_main = 0;
+      if (z_hist) {
+        B.load(rowmat(z_hist, zld), p.latent, 0, 32, 0);
+      } else {
+        B.load(rowmat_gather(obs + n.num_prop, idx, obs_stride), n.num_priv, C2_COL_PRIV, C2_COL_PRIV + pad8(n.num_priv), 0);
+        B.fwd(P + n.off_priv_w[0], n.num_priv, P + n.off_priv_b[0], n.priv_dims[0], ACT_ELU, C2_COL_PRIV, pad8(n.num_priv), 1,      // AC:219-221
+              C2PackSeg{0, 0, n.num_priv}, C2PackSeg{0, 0, 0}, C2_COL_HID, store ? p.priv[0] : nullptr, align_up(n.priv_dims[0], 4));
+        B.fwd(P + n.off_priv_w[1], n.priv_dims[0], P + n.off_priv_b[1], p.latent, ACT_ELU, C2_COL_HID, pad8(n.priv_dims[0]), 1,
+              C2PackSeg{0, 0, n.priv_dims[0]}, C2PackSeg{0, 0, 0}, 0, store ? p.priv[1] : nullptr, Lld, fin_mode == 2 ? FIN_REG : FIN_NONE, 0);
+        first_main = 2;
+      }
+      const int k0 = pad8(C2_COL_PROP + n.num_prop);
+      B.load(rowmat_gather(obs, idx, obs_stride), n.num_prop, C2_COL_PROP, k0, first_main);
+      // backbone layer 0 over cat([obs_prop, z]) (AC:211): z occupies tile columns [0, latent), obs_prop [32, 32 + num_prop)
+      B.fwd(P + n.off_actor_w[0], in0, P + n.off_actor_b[0], n.actor_dims[0], ACT_ELU, 0, k0, 2, C2PackSeg{0, n.num_prop, p.latent},
+            C2PackSeg{C2_COL_PROP, 0, n.num_prop}, 0, (store || (keep && na == 1)) ? p.ab[0] : nullptr, n.actor_dims[0], FIN_NONE, 0,
+            img_dim(n.actor_dims[0]) && (store || (keep && na == 1)));
+      int in = n.actor_dims[0];
+      for (int l = 1; l < na; ++l) {                                                   // AC:211-213
+        const bool st = store || (keep && l == na - 1);
+        B.fwd(P + n.off_actor_w[l], in, P + n.off_actor_b[l], n.actor_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
+              st ? p.ab[l] : nullptr, n.actor_dims[l], FIN_NONE, 0, img_dim(n.actor_dims[l]) && st);
+        in = n.actor_dims[l];
+      }
+      return in;
+    };
     const int fin = fin_mode == 2 ? FIN_PPO : (fin_mode == 1 ? FIN_ACT : FIN_NONE);
     float* mean = fin_mode == 0 ? p.mean : nullptr;
+    const int in = common(*A, A2 == nullptr);
     chain_head(*A, P, p.ab[na - 1], in, false, in, n.n_leg_layers, n.leg_dims, n.n_leg, n.off_aleg_w, n.off_aleg_b, p.al, store, mean, p.mean_ld, ACT_TANH, fin, 0);
-    chain_head(*A, P, p.ab[na - 1], in, true, in, n.n_arm_layers, n.arm_dims, n.n_arm, n.off_aarm_w, n.off_aarm_b, p.aa, store,
+    C2Builder& Barm = A2 ? *A2 : *A;
+    if (A2) common(*A2, false);
+    chain_head(Barm, P, p.ab[na - 1], in, A2 == nullptr, in, n.n_arm_layers, n.arm_dims, n.n_arm, n.off_aarm_w, n.off_aarm_b, p.aa, store,
                mean ? mean + n.n_leg : nullptr, p.mean_ld, ACT_TANH, fin, 1);
     A->finish();
-    if (!A->ok) return DWBC_ERR_UNSUPPORTED;
+    if (A2) A2->finish();
+    if (!A->ok || (A2 && !A2->ok)) return DWBC_ERR_UNSUPPORTED;
   }
   if (C) {
-    int in = n.num_prop + n.num_priv;
-    C->load(rowmat_gather(obs, idx, obs_stride), in, 0, pad8(in), 0);
     const int nc = n.n_critic_layers;
-    for (int l = 0; l < nc; ++l) {                                                   // AC:280-286
-      C->fwd(P + n.off_critic_w[l], in, P + n.off_critic_b[l], n.critic_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
-             (store || l == nc - 1) ? p.cb[l] : nullptr, n.critic_dims[l], FIN_NONE, 0, img_dim(n.critic_dims[l]) && (store || l == nc - 1));
-      in = n.critic_dims[l];
-    }
+    auto common = [&](C2Builder& B, bool keep) {
+      int in = n.num_prop + n.num_priv;
+      B.load(rowmat_gather(obs, idx, obs_stride), in, 0, pad8(in), 0);
+      for (int l = 0; l < nc; ++l) {                                                   // AC:280-286
+        const bool st = store || (keep && l == nc - 1);
+        B.fwd(P + n.off_critic_w[l], in, P + n.off_critic_b[l], n.critic_dims[l], ACT_ELU, 0, pad8(in), 1, C2PackSeg{0, 0, in}, C2PackSeg{0, 0, 0}, 0,
+              st ? p.cb[l] : nullptr, n.critic_dims[l], FIN_NONE, 0, img_dim(n.critic_dims[l]) && st);
+        in = n.critic_dims[l];
+      }
+      return in;
+    };
     const int fin = fin_mode == 2 ? FIN_VALUE : FIN_NONE;
+    const int in = common(*C, C2 == nullptr);
     chain_head(*C, P, p.cb[nc - 1], in, false, in, n.n_leg_layers, n.leg_dims, 1, n.off_cleg_w, n.off_cleg_b, p.cl, store, value, 2, ACT_NONE, fin, 0);
-    chain_head(*C, P, p.cb[nc - 1], in, true, in, n.n_arm_layers, n.arm_dims, 1, n.off_carm_w, n.off_carm_b, p.ca, store, value + 1, 2, ACT_NONE, fin, 1);
+    C2Builder& Barm = C2 ? *C2 : *C;
+    if (C2) common(*C2, false);
+    chain_head(Barm, P, p.cb[nc - 1], in, C2 == nullptr, in, n.n_arm_layers, n.arm_dims, 1, n.off_carm_w, n.off_carm_b, p.ca, store,
+               value + 1, 2, ACT_NONE, fin, 1);
     C->finish();
-    if (!C->ok) return DWBC_ERR_UNSUPPORTED;
+    if (C2) C2->finish();
+    if (!C->ok || (C2 && !C2->ok)) return DWBC_ERR_UNSUPPORTED;
   }
   return DWBC_OK;
 }
@@ -746,10 +770,15 @@ extern "C" int dwbc_policy_act(const DwbcNetCfg* net, const float* params, const
     pl.out = p.wpack;
     int64_t off = 0;
     const bool x3 = mlp_precision == 2;
-    C2Builder A(&pl, &off, rows, x3), C(&pl, &off, rows, x3);
-    TRY(build_forward(n, params, obs, nullptr, obs_stride, hist_encoding ? p.zh : nullptr, zld, p, values, false, 1, &A, &C));
+    C2Builder A(&pl, &off, rows, x3), C(&pl, &off, rows, x3), A2(&pl, &off, rows, x3), C2(&pl, &off, rows, x3);
+    // few tiles (the rollout): one program per HEAD, so that four short programs spread over 4 x tiles SMs (build_forward)
+    const bool split = 4 * ((rows + TC_M - 1) / TC_M) <= c2_sm_count();
+    TRY(build_forward(n, params, obs, nullptr, obs_stride, hist_encoding ? p.zh : nullptr, zld, p, values, false, 1, &A, &C, split ? &A2 : nullptr,
+                      split ? &C2 : nullptr));
+    if (off > C2_PACK_FLOATS) return DWBC_ERR_UNSUPPORTED;
     if (!weights_packed) TRY(launch_pack2(pl, st));       // the images stay valid in the workspace until the parameters change
-    return launch_chain2(&A.pr, &C.pr, fin_rollout(n, params, eps, actions, log_prob, mean, sigma, rows), x3, p.queue, st);
+    const C2Prog* prs[4] = {&A.pr, &C.pr, &A2.pr, &C2.pr};
+    return launch_chain2n(prs, split ? 4 : 2, fin_rollout(n, params, eps, actions, log_prob, mean, sigma, rows), x3, p.queue, st);
   }
   if (hist_encoding) {
     TRY(hist_forward(n, params, obs, nullptr, obs_stride, rows, p, st));
@@ -777,10 +806,12 @@ extern "C" int dwbc_critic_values(const DwbcNetCfg* net, const float* params, co
     pl.out = p.wpack;
     int64_t off = 0;
     const bool x3 = mlp_precision == 2;
-    C2Builder C(&pl, &off, rows, x3);
-    TRY(build_forward(*net, params, obs, nullptr, obs_stride, nullptr, 0, p, values, false, 0, nullptr, &C));
+    C2Builder C(&pl, &off, rows, x3), C2(&pl, &off, rows, x3);
+    const bool split = 2 * ((rows + TC_M - 1) / TC_M) <= c2_sm_count();
+    TRY(build_forward(*net, params, obs, nullptr, obs_stride, nullptr, 0, p, values, false, 0, nullptr, &C, nullptr, split ? &C2 : nullptr));
     TRY(launch_pack2(pl, st));                              // (overwrites the images a previous dwbc_policy_act left behind)
-    return launch_chain2(&C.pr, nullptr, FinArgs{}, x3, p.queue, st);
+    const C2Prog* prs[2] = {&C.pr, &C2.pr};
+    return launch_chain2n(prs, split ? 2 : 1, FinArgs{}, x3, p.queue, st);
   }
   return critic_forward(*net, params, obs, nullptr, obs_stride, rows, p, values, st);
 }

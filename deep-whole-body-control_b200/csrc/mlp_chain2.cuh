@@ -32,7 +32,7 @@
 
 namespace dwbc {
 
-constexpr int C2_MAX_OPS = 12, C2_MAX_LOADS = 6, C2_MAX_PACK = 36;   // pack items of one launch: forward + backward programs of both networks
+constexpr int C2_MAX_OPS = 12, C2_MAX_LOADS = 6, C2_MAX_PACK = 36, C2_MAX_PROGS = 4;   // pack items of one launch: forward + backward programs of both networks
 constexpr int C2_TILE = 128 * 128;                       // floats per operand tile
 constexpr int C2_WORKERS = 8;                            // epilogue / load warps: lane quarter = warp % 4, column group = warp / 4
 constexpr int C2_H = C2_WORKERS / 4;                     // column groups: a warp takes the 32-column chunks ci with ci % C2_H == its group
@@ -104,7 +104,7 @@ struct C2Launch {
   // (launch_chain2 picks ns1 by simulating the queue on the SM count)
   int np2, ns1;
   int* queue;                // [2] device counters (next item, finished CTAs), zero between launches
-  C2Prog p[2];
+  C2Prog p[C2_MAX_PROGS];
   FinArgs fin;
 };
 
@@ -1002,12 +1002,14 @@ inline int c2_pick_singles(int tiles, int nprog, const double* cost, int sms) {
     return s1;
   }
   if (c2_single_penalty <= 0.0) return 0;
-  struct Key { int tiles, nprog, sms; double c0, c1, pen; int ns1; };
+  struct Key { int tiles, nprog, sms; double c0, c1, pen; int ns1; };       // (c1: the sum of the other programs' costs)
   static thread_local Key cache[8];
   static thread_local int ncache = 0;
+  double rest = 0.0;
+  for (int k = 1; k < nprog; ++k) rest += cost[k] * (1.0 + 1e-3 * k);
   for (int i = 0; i < ncache; ++i) {
     const Key& k = cache[i];
-    if (k.tiles == tiles && k.nprog == nprog && k.sms == sms && k.c0 == cost[0] && k.c1 == cost[1] && k.pen == c2_single_penalty) return k.ns1;
+    if (k.tiles == tiles && k.nprog == nprog && k.sms == sms && k.c0 == cost[0] && k.c1 == rest && k.pen == c2_single_penalty) return k.ns1;
   }
   int best = 0;
   double best_t = c2_makespan(tiles, nprog, cost, sms, 0);
@@ -1016,18 +1018,37 @@ inline int c2_pick_singles(int tiles, int nprog, const double* cost, int sms) {
     if (t < best_t * (1.0 - 1e-9)) { best_t = t; best = s1; }
   }
   Key& k = cache[ncache < 8 ? ncache++ : 7];
-  k = Key{tiles, nprog, sms, cost[0], cost[1], c2_single_penalty, best};
+  k = Key{tiles, nprog, sms, cost[0], rest, c2_single_penalty, best};
   return best;
 }
 
+inline int c2_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+inline int launch_chain2n(const C2Prog* const* prs, int nprog, const FinArgs& fin, bool x3, int* queue, cudaStream_t st);
 inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fin, bool x3, int* queue, cudaStream_t st) {
+  const C2Prog* prs[2] = {pr0, pr1};
+  return launch_chain2n(prs, pr1 ? 2 : 1, fin, x3, queue, st);
+}
+// up to C2_MAX_PROGS programs over the same rows in one launch; queued longest program first
+inline int launch_chain2n(const C2Prog* const* prs, int nprog, const FinArgs& fin, bool x3, int* queue, cudaStream_t st) {
+  if (nprog < 1 || nprog > C2_MAX_PROGS) return DWBC_ERR_ARG;
   C2Launch L{};
-  L.nprog = pr1 ? 2 : 1;
+  L.nprog = nprog;
   L.x3 = x3 ? 1 : 0;
   L.queue = queue;
   L.fin = fin;
-  if (pr1 && pr1->n_ops > pr0->n_ops) { L.p[0] = *pr1; L.p[1] = *pr0; }
-  else { L.p[0] = *pr0; if (pr1) L.p[1] = *pr1; }
+  int order[C2_MAX_PROGS];
+  for (int k = 0; k < nprog; ++k) order[k] = k;
+  std::stable_sort(order, order + nprog, [&](int a, int b) { return prs[a]->n_ops > prs[b]->n_ops; });
+  for (int k = 0; k < nprog; ++k) L.p[k] = *prs[order[k]];
   for (int k = 0; k < L.nprog; ++k) {
     const C2Prog& pr = L.p[k];
     if (pr.M <= 0 || pr.M != L.p[0].M || pr.n_ops <= 0 || pr.n_ops > C2_MAX_OPS || pr.n_loads < 0 || pr.n_loads > C2_MAX_LOADS) return DWBC_ERR_ARG;
@@ -1037,18 +1058,14 @@ inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fi
   for (int k = 0; k < L.nprog; ++k)
     for (int i = 0; i < L.p[k].n_ops; ++i) L.p[k].op[i].y = nullptr;
 #endif
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = c2_sm_count();
   const int tiles = (L.p[0].M + TC_M - 1) / TC_M;
   if (tiles * L.nprog <= sms) {                            // small batches (rollout): one tile per item, spread over more SMs
     L.np2 = 0;
     L.ns1 = tiles;
   } else {
-    double cost[2] = {c2_prog_cost(L.p[0]), L.nprog > 1 ? c2_prog_cost(L.p[1]) : 0.0};
+    double cost[C2_MAX_PROGS] = {};
+    for (int k = 0; k < L.nprog; ++k) cost[k] = c2_prog_cost(L.p[k]);
     L.ns1 = c2_pick_singles(tiles, L.nprog, cost, sms);
     L.np2 = (tiles - L.ns1 + 1) / 2;
   }

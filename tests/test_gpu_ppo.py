@@ -308,7 +308,7 @@ def test_stock_policy_shape_512_256_128_matches_oracle_autograd(precision):
     ref_act = PO.policy_act(P, obs[0], eps)
     alg.act(obs[0].cuda(), obs[0].cuda(), False, eps=eps.cuda())
     s = alg.storage
-    tol_f = 2e-2 if precision == "tf32" else 2e-5
+    tol_f = 1e-3 if precision == "tf32" else 2e-5      # measured on B200: 2.7e-4 (tf32: only the 128-wide layers run on the tensor cores), 1e-7
     e_mean = float((s.mu[0].cpu() - ref_act["mean"]).abs().max())
     e_val = float((s.values[0].cpu() - ref_act["values"]).abs().max())
     assert e_mean < tol_f and e_val < tol_f * max(1.0, float(ref_act["values"].abs().max())), (e_mean, e_val)
@@ -334,7 +334,7 @@ def test_stock_policy_shape_512_256_128_matches_oracle_autograd(precision):
                                             L.stream_ptr()), "grad")
     got = ac.unflat(alg.grad)
     worst = 0.0
-    tol_g = 5e-2 if precision == "tf32" else 2e-3
+    tol_g = 1e-2 if precision == "tf32" else 2e-3      # measured: 3.3e-3 (tf32), 1.6e-6 (fp32 / tf32x3)
     for n in P:
         ref = P[n].grad if P[n].grad is not None else torch.zeros_like(P[n])
         scale = max(float(ref.abs().max()), 1e-6)
