@@ -869,7 +869,7 @@ extern "C" int dwbc_ppo_minibatch_grad(const DwbcNetCfg* net, const float* param
     f.ts_w = hp->torque_supervision_weight;
     TRY(launch_pack2(pl, st));
     TRY(launch_chain2(&A.pr, &C.pr, f, x3, p.queue, st));
-    TRY(launch_chain2(&Ab.pr, &Cb.pr, FinArgs{}, x3, p.queue, st));
+    TRY(launch_chain2(&Ab.pr, &Cb.pr, FinArgs{}, x3, p.queue, st, c2_bwd_reverse != 0));
     return weight_gradients(n, grad, s, idx, rows, p, st);
   }
   TRY(priv_forward(n, P, s->observations, idx, s->obs_stride, rows, p, st));
@@ -1029,6 +1029,14 @@ extern "C" int dwbc_debug_set_chain_single_penalty(double v) {
 // tuning aid: deal of the grouped weight-gradient work items (1 = sorted + boustrophedon, 0 = round-robin in construction order)
 extern "C" int dwbc_debug_set_wgrad_snake(int on) {
   wg_snake = on ? 1 : 0;
+  return DWBC_OK;
+}
+extern "C" int dwbc_debug_set_chain_bwd_reverse(int on) {
+  c2_bwd_reverse = on ? 1 : 0;
+  return DWBC_OK;
+}
+extern "C" int dwbc_debug_set_wgrad_reverse(int on) {
+  wg_reverse = on ? 1 : 0;
   return DWBC_OK;
 }
 extern "C" int dwbc_debug_set_wgrad_items(int per_cta) {

@@ -103,6 +103,7 @@ struct C2Launch {
   // every program, longest program first) are queued in front of all one-tile items: the tail of a launch is filled with half-size items
   // (launch_chain2 picks ns1 by simulating the queue on the SM count)
   int np2, ns1;
+  int rev;                   // tiles are taken from the last one downwards
   int* queue;                // [2] device counters (next item, finished CTAs), zero between launches
   C2Prog p[C2_MAX_PROGS];
   FinArgs fin;
@@ -515,6 +516,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
       nslots = min(two ? 2 : 1, tiles - t0);
       asm volatile("" : "+r"(nslots));                   // opaque: one body for both item sizes (the compiler cloned the whole item loop otherwise)
     }
+    // slot s works on tile tb + s * td: upwards from t0, or (L.rev: the backward launch) downwards from the last tile -- the forward launch
+    // that produced the activation images this one reads walked upwards, so its most recent output, still in L2, belongs to the last tiles
+    const int tb = L.rev ? tiles - 1 - t0 : t0, td = L.rev ? -1 : 1;
     // the item's program goes to shared memory: read through the kernel parameter, every field access with a run-time op index is an
     // indexed constant-bank load (LDC c[0x0][R + off]) -- a long-scoreboard stall in front of most addresses and predicates of the epilogue
     if (pi != cur_prog) {
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
           const uint32_t a0 = tc_smem_u32(tile[s]) + (uint32_t)(o.a_col0 >> 2) * 128u;
           const uint32_t dt = tmem + s * 256;
           if (c2_elect()) {
-            if (st_prev) c2_bulk_s2g(pr.op[i - 1].y + (size_t)(t0 + s) * C2_TILE, tile[s], C2_TILE * 4);
+            if (st_prev) c2_bulk_s2g(pr.op[i - 1].y + (size_t)(tb + s * td) * C2_TILE, tile[s], C2_TILE * 4);
             // one K step (8 columns = two 16-byte pieces) advances both start addresses by 256 bytes: +16 in the descriptors' address field
             uint64_t ad = tc_desc(a0, 128, 4096), bd = tc_desc(b0, 128, wsbo);
             tc_mma_tf32(dt, ad, bd, idesc, 0u);
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         tc_mbar_wait(&sh.ready[s], (rcnt[s] + nops) & 1);
         tc_fence_async_smem();
         if (c2_elect()) {
-          if (pr.op[nops - 1].y_img) c2_bulk_s2g(pr.op[nops - 1].y + (size_t)(t0 + s) * C2_TILE, tile[s], C2_TILE * 4);
+          if (pr.op[nops - 1].y_img) c2_bulk_s2g(pr.op[nops - 1].y + (size_t)(tb + s * td) * C2_TILE, tile[s], C2_TILE * 4);
           if (s + 1 == nslots) c2_bulk_wait_read();
         }
         __syncwarp();
@@ -682,7 +686,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         if (sync_first) c2_wbar();                       // every worker has finished writing / copying the tiles the loads overwrite
         int nimg = 0;
         for (int s = 0; s < nslots; ++s) {
-          const int64_t m0 = (int64_t)(t0 + s) * TC_M;
+          const int64_t m0 = (int64_t)(tb + s * td) * TC_M;
           const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
           for (int l = 0; l < pr.n_loads; ++l) {
             if (pr.ld[l].before_op != before) continue;
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
             c2_expect_tx(&sh.ld_bar, (uint32_t)nimg * C2_TILE * 4u);
             for (int s = 0; s < nslots; ++s)
               for (int l = 0; l < pr.n_loads; ++l)
-                if (pr.ld[l].before_op == before && pr.ld[l].img) c2_bulk_g2s(tile[s], pr.ld[l].src.p + (size_t)(t0 + s) * C2_TILE, C2_TILE * 4, &sh.ld_bar);
+                if (pr.ld[l].before_op == before && pr.ld[l].img) c2_bulk_g2s(tile[s], pr.ld[l].src.p + (size_t)(tb + s * td) * C2_TILE, C2_TILE * 4, &sh.ld_bar);
           }
           tc_mbar_wait(&sh.ld_bar, nld & 1);
           ++nld;
@@ -716,7 +720,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         const C2Load& ld = pr.ld[l];
         if (ld.before_op == 0 || ld.img) continue;
         for (int s = 0; s < nslots; ++s) {
-          const int64_t m0 = (int64_t)(t0 + s) * TC_M;
+          const int64_t m0 = (int64_t)(tb + s * td) * TC_M;
           if (m0 + lrow >= pr.M) continue;
           const float* src = ld.src.row(m0 + lrow);
           for (int b = lpc * 32; b < ld.ncols; b += LPS * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + b));
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
         bool pending = false;                              // loads that precede op i+1 cover both slots and follow the last slot's epilogue
         for (int l = 0; l < pr.n_loads; ++l) pending |= pr.ld[l].before_op == i + 1;
         for (int s = 0; s < nslots; ++s) {
-          const int64_t m0 = (int64_t)(t0 + s) * TC_M;
+          const int64_t m0 = (int64_t)(tb + s * td) * TC_M;
           const int rows = (int)min((int64_t)TC_M, (int64_t)pr.M - m0);
           const bool on = r < rows;
           // backward: the activation chunks whose derivative multiplies, fetched while the MMAs run
@@ -743,7 +747,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) chain2_kernel(const __grid_cons
             for (int u = 0; u < C2_CPW; ++u) {
               const int c0 = 32 * (h + u * C2_H);
               // row-major: 32 consecutive floats of the row; tile image: eight 16-byte pieces 128 bytes apart (eight rows share each line)
-              const float* xr = o.x_img ? o.xact + (size_t)(t0 + s) * C2_TILE + ((size_t)((r >> 3) * 32 + (c0 >> 2)) * 8 + (r & 7)) * 4
+              const float* xr = o.x_img ? o.xact + (size_t)(tb + s * td) * C2_TILE + ((size_t)((r >> 3) * 32 + (c0 >> 2)) * 8 + (r & 7)) * 4
                                         : o.xact + (m0 + r) * o.ldx + c0;
               const int xst = o.x_img ? 32 : 4;
 #pragma unroll
@@ -1032,15 +1036,17 @@ inline int c2_sm_count() {
   return sms;
 }
 
-inline int launch_chain2n(const C2Prog* const* prs, int nprog, const FinArgs& fin, bool x3, int* queue, cudaStream_t st);
-inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fin, bool x3, int* queue, cudaStream_t st) {
+inline int c2_bwd_reverse = 1;                            // tuning aid (dwbc_debug_set_chain_bwd_reverse): the backward launch walks the tiles downwards
+inline int launch_chain2n(const C2Prog* const* prs, int nprog, const FinArgs& fin, bool x3, int* queue, cudaStream_t st, bool rev = false);
+inline int launch_chain2(const C2Prog* pr0, const C2Prog* pr1, const FinArgs& fin, bool x3, int* queue, cudaStream_t st, bool rev = false) {
   const C2Prog* prs[2] = {pr0, pr1};
-  return launch_chain2n(prs, pr1 ? 2 : 1, fin, x3, queue, st);
+  return launch_chain2n(prs, pr1 ? 2 : 1, fin, x3, queue, st, rev);
 }
 // up to C2_MAX_PROGS programs over the same rows in one launch; queued longest program first
-inline int launch_chain2n(const C2Prog* const* prs, int nprog, const FinArgs& fin, bool x3, int* queue, cudaStream_t st) {
+inline int launch_chain2n(const C2Prog* const* prs, int nprog, const FinArgs& fin, bool x3, int* queue, cudaStream_t st, bool rev) {
   if (nprog < 1 || nprog > C2_MAX_PROGS) return DWBC_ERR_ARG;
   C2Launch L{};
+  L.rev = rev ? 1 : 0;
   L.nprog = nprog;
   L.x3 = x3 ? 1 : 0;
   L.queue = queue;

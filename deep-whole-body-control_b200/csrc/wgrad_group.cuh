@@ -40,7 +40,10 @@ struct WGItem {
 // widowGo1 mini-batch.  MEASURED SLOWER on B200 (update() 21.83 against 21.12 ms, 3xTF32; 17.36 against 16.92 ms, TF32): GEMM-major
 // order makes all 148 CTAs reduce into the SAME 64 KB dW at the same time (red.global.add contention in L2), round-robin spreads the
 // epilogues of one moment over all 17 GEMMs.
-struct WGroup { int n, rows, slab, nslab, snake; WGItem it[WG_MAX]; };
+// rev != 0: slabs are taken from the LAST rows to the first.  The backward chain that runs right before this kernel walks the tiles upwards, so
+// its most recent writes (dZ images) and reads (activation images) -- the part of the 0.5 GB working set that is still in the 126 MB L2 --
+// belong to the last rows; walking upwards too, this kernel started with the rows that had been evicted longest ago.
+struct WGroup { int n, rows, slab, nslab, snake, rev; WGItem it[WG_MAX]; };
 
 // elect.sync: true in exactly one lane of the (converged) warp
 __device__ __forceinline__ bool wg_elect() {
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_group_kernel(const __grid
       slab_i = w / grp.n;
     }
     const WGItem& g = grp.it[layer];
+    if (grp.rev) slab_i = grp.nslab - 1 - slab_i;
     const int64_t k_begin = (int64_t)slab_i * grp.slab;
     const int64_t k_end = min((int64_t)grp.rows, k_begin + grp.slab);
     const int nch = (int)((k_end - k_begin + WCH - 1) / WCH);
@@ -413,11 +417,13 @@ struct WGroupBuilder {
 };
 
 inline int wg_items_per_cta = 4;                     // tuning aid (dwbc_debug_set_wgrad_items)
+inline int wg_reverse = 0;                            // tuning aid (dwbc_debug_set_wgrad_reverse): 0 = slabs from the first rows upwards
 inline int wg_snake = 0;                             // tuning aid (dwbc_debug_set_wgrad_snake): 0 = round-robin deal in construction order
 
 inline int launch_wgrad_group(WGroup& g, int rows, bool x3, cudaStream_t st) {
   if (g.n <= 0 || rows <= 0) return DWBC_ERR_ARG;
   g.snake = wg_snake;
+  g.rev = wg_reverse;
   if (g.snake)         // widest operand pair first (a work item's time goes with the bytes it fetches per row)
     std::stable_sort(g.it, g.it + g.n, [](const WGItem& a, const WGItem& b) {
       return ((a.Mo + 15) & ~15) + ((a.Ni + 15) & ~15) > ((b.Mo + 15) & ~15) + ((b.Ni + 15) & ~15);

@@ -26,6 +26,11 @@ int dwbc_debug_set_chain_singles(int n);
 /* Deal of the grouped weight-gradient work items (wgrad_group.cuh): 0 = round-robin in construction order (default), 1 = GEMMs
  * sorted by operand width, items dealt boustrophedon (measured slower: all CTAs reduce into the same dW at the same time) */
 int dwbc_debug_set_wgrad_snake(int on);
+/* tile order of the backward chain launch: 1 = from the last tile downwards (default), 0 = upwards */
+int dwbc_debug_set_chain_bwd_reverse(int on);
+/* slab order of the grouped weight-gradient launch: 1 = from the last rows downwards (default: the rows the backward chain touched last
+ * are still in L2), 0 = upwards */
+int dwbc_debug_set_wgrad_reverse(int on);
 /* work items per CTA the slab length of the grouped weight-gradient launch aims at (default 4) */
 int dwbc_debug_set_wgrad_items(int per_cta);
 

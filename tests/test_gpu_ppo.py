@@ -436,26 +436,34 @@ def test_fused_chain_forward_matches_fp32_path_many_tiles(hist, precision):
     assert all(torch.isfinite(t).all() for t in out[precision])
 
 
-@pytest.mark.parametrize("singles,snake", [(-1, 1), (0, 0), (37, 1), (-1, 0)])
+@pytest.mark.parametrize("singles,snake,rev", [(-1, 0, 1), (0, 0, 0), (37, 1, 1), (-1, 1, 0)])
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
-def test_fused_chain_backward_matches_fp32_path_many_tiles(precision, singles, snake):
+def test_fused_chain_backward_matches_fp32_path_many_tiles(precision, singles, snake, rev):
     """Mini-batch gradient through the fused forward chains (loss in the epilogue), backward chains and the MN-major weight-gradient GEMMs
     against the exact-fp32 layer-wise path of the same library, at a row count that gives every CTA several tile pairs plus a ragged one.
     Tolerances: CHAIN_TOL, per parameter tensor ||g - g_fp32|| <= tol ||g_fp32|| (+ 1e-7 abs).
     `singles`: one-tile work items per program at the tail of the chain launches (-1: the planner of launch_chain2 decides, 0: two-tile
     items only -- the odd last pair then holds one tile --, 37: forced, the ragged last tile runs as a one-tile item); `snake`: deal of
-    the grouped weight-gradient work items (1: sorted by operand width, boustrophedon; 0: round-robin in construction order)."""
+    the grouped weight-gradient work items (1: sorted by operand width, boustrophedon; 0: round-robin in construction order); `rev`: its
+    slab order (1: from the last rows downwards; 0: upwards, the default); the backward chain launch walks the tiles the other way round
+    (dwbc_debug_set_chain_bwd_reverse: downwards by default, after the forward launch that walked upwards)."""
     import ctypes as C
     from dwbc_b200 import _lib as L
     L.lib().dwbc_debug_set_chain_singles.argtypes = [C.c_int]
     L.lib().dwbc_debug_set_wgrad_snake.argtypes = [C.c_int]
     L.lib().dwbc_debug_set_chain_singles(singles)
     L.lib().dwbc_debug_set_wgrad_snake(snake)
+    L.lib().dwbc_debug_set_wgrad_reverse.argtypes = [C.c_int]
+    L.lib().dwbc_debug_set_wgrad_reverse(rev)
+    L.lib().dwbc_debug_set_chain_bwd_reverse.argtypes = [C.c_int]
+    L.lib().dwbc_debug_set_chain_bwd_reverse(1 - rev)
     try:
         _chain_backward_many_tiles(precision)
     finally:
         L.lib().dwbc_debug_set_chain_singles(-1)
         L.lib().dwbc_debug_set_wgrad_snake(0)
+        L.lib().dwbc_debug_set_wgrad_reverse(0)
+        L.lib().dwbc_debug_set_chain_bwd_reverse(1)
 
 
 def _chain_backward_many_tiles(precision):
