@@ -1026,6 +1026,17 @@ extern "C" int dwbc_debug_set_chain_single_penalty(double v) {
   c2_single_penalty = v;
   return DWBC_OK;
 }
+// The work-item planner of launch_chain2n on its own (host code only, no GPU): for `tiles` row tiles x `nprog` programs of per-two-tile-item
+// costs cost[nprog] on `sms` persistent CTAs, the number of two-tile (np2) and one-tile (ns1) items per program it would launch and the
+// simulated makespans with (span) and without (span0) one-tile items.  tests/test_host_cpu.py checks coverage and the decision.
+extern "C" int dwbc_debug_chain_plan(int tiles, int nprog, const double* cost, int sms, int* np2, int* ns1, double* span, double* span0) {
+  if (tiles <= 0 || nprog < 1 || nprog > C2_MAX_PROGS || !cost || sms <= 0 || !np2 || !ns1) return DWBC_ERR_ARG;
+  if (tiles * nprog <= sms) { *np2 = 0; *ns1 = tiles; }
+  else { *ns1 = c2_pick_singles(tiles, nprog, cost, sms); *np2 = (tiles - *ns1 + 1) / 2; }
+  if (span) *span = c2_makespan(tiles, nprog, cost, sms, *np2 ? *ns1 : 0);
+  if (span0) *span0 = c2_makespan(tiles, nprog, cost, sms, 0);
+  return DWBC_OK;
+}
 // tuning aid: deal of the grouped weight-gradient work items (1 = sorted + boustrophedon, 0 = round-robin in construction order)
 extern "C" int dwbc_debug_set_wgrad_snake(int on) {
   wg_snake = on ? 1 : 0;

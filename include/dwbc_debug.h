@@ -22,6 +22,8 @@ int dwbc_debug_set_cycle_buffer(unsigned long long* dev_ptr);
  * (<= 0: no one-tile items at the tail of a large launch), and a forced number of one-tile items per program (-1: planner decides) */
 int dwbc_debug_set_chain_single_penalty(double ratio);
 int dwbc_debug_set_chain_singles(int n);
+/* the planner on its own (host code, no GPU): items per program and simulated makespans with / without one-tile items */
+int dwbc_debug_chain_plan(int tiles, int nprog, const double* cost, int sms, int* np2, int* ns1, double* span, double* span0);
 
 /* Deal of the grouped weight-gradient work items (wgrad_group.cuh): 0 = round-robin in construction order (default), 1 = GEMMs
  * sorted by operand width, items dealt boustrophedon (measured slower: all CTAs reduce into the same dW at the same time) */

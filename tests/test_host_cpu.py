@@ -66,6 +66,37 @@ def test_torque_supervision_host_side():
     assert off.storage.target_arm_torques is None and not off.storage._c.target_arm_torques and off._fill_hp().arm_coefs is None
 
 
+def test_chain_work_item_planner_host_logic():
+    """launch_chain2n's planner (mlp_chain2.cuh, host code): every tile of every program is covered exactly once by the two-tile items
+    [0, 2 np2) and the one-tile items behind them; one-tile items are only used when the simulated queue gets shorter; the bench shape
+    (320 tiles x {actor, critic} on 148 SMs) gets a tail of one-tile items, small launches get one tile per item."""
+    import ctypes as C
+    from dwbc_b200 import _lib as L
+    lib = L.lib()
+    lib.dwbc_debug_chain_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
+
+    def plan(tiles, costs, sms=148):
+        c = (C.c_double * 4)(*(list(costs) + [0.0] * (4 - len(costs))))
+        np2, ns1, span, span0 = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        assert lib.dwbc_debug_chain_plan(tiles, len(costs), c, sms, C.byref(np2), C.byref(ns1), C.byref(span), C.byref(span0)) == 0
+        return np2.value, ns1.value, span.value, span0.value
+
+    for tiles in (1, 2, 37, 74, 75, 149, 299, 320, 321, 640, 1000):
+        for costs in ((9.6, 7.65), (9.0,), (6.0, 6.0, 4.0, 4.0)):
+            np2, ns1, span, span0 = plan(tiles, costs)
+            if tiles * len(costs) <= 148:
+                assert (np2, ns1) == (0, tiles)                     # one tile per item, spread over the SMs
+                continue
+            assert ns1 == 0 or 2 * np2 + ns1 == tiles               # whole pairs in front of the one-tile items
+            assert 2 * np2 + ns1 >= tiles and 2 * (np2 - 1) + ns1 < tiles
+            assert span <= span0 * (1 + 1e-12)
+    np2, ns1, span, span0 = plan(320, (9.6, 7.65))                  # the flat-config mini-batch: 40 960 rows
+    assert ns1 >= 48 and span < 0.92 * span0
+    assert plan(320, (9.6, 7.65), sms=160)[1] == 0                  # 160 pairs per program on 160 CTAs: two full waves, nothing to fill
+    assert lib.dwbc_debug_chain_plan(0, 2, None, 148, None, None, None, None) == -1
+
+
 def test_checkpoint_round_trip_keeps_reference_names_and_shapes():
     """OPR:276-290: model_state_dict / optimizer_state_dict.  Names and order are the reference ActorCritic's (pinned by the golden file)."""
     g = np.load(os.path.join(G, "ppo.npz"))
