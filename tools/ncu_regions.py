@@ -40,7 +40,8 @@ for cub in glob.glob(os.path.join(tmp, "*.cubin")):
 assert ins, "kernel not found in " + so
 
 # ---- per-instruction samples of the chosen launch ----
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre, "--launch-skip", str(launch), "--launch-count", "1"],
+                     capture_output=True, text=True).stdout
 secs = []
 for r in csv.reader(io.StringIO(out)):
     if r and r[0] == "Kernel Name":
@@ -49,7 +50,7 @@ for r in csv.reader(io.StringIO(out)):
         secs[-1]["hdr"] = r
     elif secs and secs[-1]["hdr"] and len(r) >= len(secs[-1]["hdr"]) - 2:
         secs[-1]["data"].append(r)
-s = secs[launch]
+s = secs[0]          # (ncu prints the selected launch's table once per source view)
 hdr, data = s["hdr"], s["data"]
 assert len(data) == len(ins), f"profile ({len(data)} instructions) and library ({len(ins)}) come from different builds"
 ia, isamp, iex, isrc = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Source")
