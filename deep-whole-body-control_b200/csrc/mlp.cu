@@ -1026,6 +1026,63 @@ extern "C" int dwbc_debug_set_chain_single_penalty(double v) {
   c2_single_penalty = v;
   return DWBC_OK;
 }
+// The chain PROGRAMS a call would launch, described without launching anything (host code only, no GPU; every pointer is formed from the
+// fake bases below and never dereferenced).  what: 0 = dwbc_policy_act, 1 = dwbc_critic_values, 2 = forward + loss of dwbc_ppo_minibatch_grad,
+// 3 = its backward launch.  out = [nprog, pack items, then per program: n_ops, n_loads, then per op: N, kpad, act, fin, fin_c, out_col0,
+// has_global_output, output_is_tile_image].  Returns the number of ints written, or a negative error code (DWBC_ERR_UNSUPPORTED: the
+// configuration does not run on the fused chains).  tests/test_host_cpu.py pins the program structure with it.
+extern "C" int dwbc_debug_describe_chain(const DwbcNetCfg* net, int32_t rows, int what, int hist_encoding, int sms, int32_t* out, int32_t out_len) {
+  TRY(check_net(net));
+  if (rows <= 0 || what < 0 || what > 3 || sms <= 0 || !out) return DWBC_ERR_ARG;
+  const DwbcNetCfg& n = *net;
+  float* const ws = reinterpret_cast<float*>(uintptr_t(1) << 40);
+  const float* const P = reinterpret_cast<const float*>(uintptr_t(2) << 40);
+  const float* const obs = reinterpret_cast<const float*>(uintptr_t(3) << 40);
+  const int64_t* const idx = what >= 2 ? reinterpret_cast<const int64_t*>(uintptr_t(4) << 40) : nullptr;
+  Plan p = make_plan(n, rows, ws);
+  if (!chain_usable(n, p, obs, n.num_obs)) return DWBC_ERR_UNSUPPORTED;
+  C2PackList pl{};
+  pl.out = p.wpack;
+  int64_t off = 0;
+  const bool x3 = mlp_precision == 2;
+  C2Builder A(&pl, &off, rows, x3), C(&pl, &off, rows, x3), A2(&pl, &off, rows, x3), C2(&pl, &off, rows, x3);
+  const C2Prog* prs[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nprog = 0;
+  const int tiles = (rows + TC_M - 1) / TC_M, zld = (int)align_up(p.latent, 4);
+  if (what == 0) {
+    const bool split = 4 * tiles <= sms;
+    TRY(build_forward(n, P, obs, nullptr, n.num_obs, hist_encoding ? p.zh : nullptr, zld, p, p.value, false, 1, &A, &C, split ? &A2 : nullptr, split ? &C2 : nullptr));
+    prs[0] = &A.pr; prs[1] = &C.pr; prs[2] = &A2.pr; prs[3] = &C2.pr;
+    nprog = split ? 4 : 2;
+  } else if (what == 1) {
+    const bool split = 2 * tiles <= sms;
+    TRY(build_forward(n, P, obs, nullptr, n.num_obs, nullptr, 0, p, p.value, false, 0, nullptr, &C, nullptr, split ? &C2 : nullptr));
+    prs[0] = &C.pr; prs[1] = &C2.pr;
+    nprog = split ? 2 : 1;
+  } else {
+    C2Builder Ab(&pl, &off, rows, x3), Cb(&pl, &off, rows, x3);
+    TRY(build_forward(n, P, obs, idx, n.num_obs, nullptr, zld, p, p.value, true, 2, &A, &C));
+    TRY(build_backward(n, P, p, Ab, Cb));
+    static C2Prog keep[2];                 // (the builders of this branch go out of scope)
+    keep[0] = what == 2 ? A.pr : Ab.pr; keep[1] = what == 2 ? C.pr : Cb.pr;
+    prs[0] = &keep[0]; prs[1] = &keep[1];
+    nprog = 2;
+  }
+  if (off > C2_PACK_FLOATS) return DWBC_ERR_UNSUPPORTED;
+  int k = 0;
+  auto put = [&](int v) { if (k < out_len) out[k] = v; ++k; };
+  put(nprog); put(pl.n);
+  for (int q = 0; q < nprog; ++q) {
+    const C2Prog& pr = *prs[q];
+    put(pr.n_ops); put(pr.n_loads);
+    for (int i = 0; i < pr.n_ops; ++i) {
+      const C2Op& o = pr.op[i];
+      put(o.N); put(o.kpad); put(o.act); put(o.fin); put(o.fin_c); put(o.out_col0); put(o.y != nullptr); put(o.y_img);
+    }
+  }
+  return k <= out_len ? k : DWBC_ERR_ARG;
+}
+
 // The work-item planner of launch_chain2n on its own (host code only, no GPU): for `tiles` row tiles x `nprog` programs of per-two-tile-item
 // costs cost[nprog] on `sms` persistent CTAs, the number of two-tile (np2) and one-tile (ns1) items per program it would launch and the
 // simulated makespans with (span) and without (span0) one-tile items.  tests/test_host_cpu.py checks coverage and the decision.

@@ -22,6 +22,10 @@ int dwbc_debug_set_cycle_buffer(unsigned long long* dev_ptr);
  * (<= 0: no one-tile items at the tail of a large launch), and a forced number of one-tile items per program (-1: planner decides) */
 int dwbc_debug_set_chain_single_penalty(double ratio);
 int dwbc_debug_set_chain_singles(int n);
+/* The chain programs a call would launch, described without launching (host code, no GPU).  what: 0 = dwbc_policy_act, 1 = dwbc_critic_values,
+ * 2 / 3 = forward + loss / backward launch of dwbc_ppo_minibatch_grad.  out = [nprog, pack items, per program: n_ops, n_loads, per op: N, kpad,
+ * act, fin, fin_c, out_col0, has_global_output, output_is_tile_image]; returns the number of ints written or a negative DWBC_ERR_*. */
+int dwbc_debug_describe_chain(const DwbcNetCfg* net, int32_t rows, int what, int hist_encoding, int sms, int32_t* out, int32_t out_len);
 /* the planner on its own (host code, no GPU): items per program and simulated makespans with / without one-tile items */
 int dwbc_debug_chain_plan(int tiles, int nprog, const double* cost, int sms, int* np2, int* ns1, double* span, double* span0);
 

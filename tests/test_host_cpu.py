@@ -97,6 +97,63 @@ def test_chain_work_item_planner_host_logic():
     assert lib.dwbc_debug_chain_plan(0, 2, None, 148, None, None, None, None) == -1
 
 
+def test_chain_programs_host_logic():
+    """The layer-chain PROGRAMS the entry points build (mlp.cu: build_forward / build_backward; host code, described by
+    dwbc_debug_describe_chain without a GPU): a 4096-row rollout is four programs, one per head, of at most 6 ops (AC:204-217, 280-286); above
+    37 tiles the heads share a program; update(): the loss hooks sit on the heads' last ops (PPO:166-221); fp32 precision does not use the chains."""
+    import ctypes as C
+    from dwbc_b200 import _lib as L
+    lib = L.lib()
+    lib.dwbc_debug_describe_chain.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int32]
+    ac = FlatActorCritic(device="cpu", num_priv=24, num_hist=10, num_prop=76)
+    FIN_ACT, FIN_PPO, FIN_VALUE, FIN_REG, ELU, TANH = 1, 2, 3, 4, 1, 2
+
+    def describe(rows, what, hist=0, precision="tf32x3", sms=148):
+        ac.net_cfg.precision = L.PRECISIONS[precision]
+        out = (C.c_int32 * 512)()
+        k = lib.dwbc_debug_describe_chain(C.addressof(ac.net_cfg), rows, what, hist, sms, out, 512)
+        if k < 0:
+            return k
+        v, i, progs = list(out[:k]), 2, []
+        for _ in range(out[0]):
+            n_ops, n_loads = v[i], v[i + 1]
+            i += 2
+            progs.append((n_loads, [dict(zip(("N", "kpad", "act", "fin", "fin_c", "out_col0", "y", "y_img"), v[i + 8 * j:i + 8 * j + 8])) for j in range(n_ops)]))
+            i += 8 * n_ops
+        assert i == k
+        return v[1], progs
+
+    widths = lambda prog: [o["N"] for o in prog[1]]  # noqa: E731
+    fins = lambda prog: [(o["fin"], o["fin_c"]) for o in prog[1] if o["fin"]]  # noqa: E731
+    # ---- rollout, 4096 rows: one program per head ----
+    npack, progs = describe(4096, 0)
+    assert npack == 20 and len(progs) == 4
+    assert sorted(map(widths, progs)) == sorted([[64, 20, 128, 128, 128, 12], [64, 20, 128, 128, 128, 6], [128, 128, 128, 1], [128, 128, 128, 1]])
+    assert sorted(f for p in progs for f in fins(p)) == [(FIN_ACT, 0), (FIN_ACT, 1)]          # sampling + log-prob on the two action heads only
+    assert all(o["y"] == 0 or o["N"] <= 2 for p in progs for o in p[1])                         # nothing but the values leaves a rollout program by stores
+    assert [o["act"] for o in progs[0][1]] == [ELU] * 5 + [TANH]                                # AC:157,170: tanh on the action means
+    # ---- the same with the history-encoder latent (student rollouts): no privileged encoder in the programs ----
+    _, progs_h = describe(4096, 0, hist=1)
+    assert sorted(map(widths, progs_h)) == sorted([[128, 128, 128, 12], [128, 128, 128, 6], [128, 128, 128, 1], [128, 128, 128, 1]])
+    # ---- 8192 rows (ROA): 64 tiles x 4 programs would not fit the SMs -> the heads share a program again ----
+    npack, progs = describe(8192, 0)
+    assert npack == 16 and list(map(widths, progs)) == [[64, 20, 128, 128, 128, 12, 128, 128, 6], [128, 128, 128, 1, 128, 128, 1]]
+    assert progs[0][0] == 3 and progs[1][0] == 2                                                # gathers + the trunk reload of the second head
+    assert len(describe(4096, 0, sms=100)[1]) == 2                                              # (the split follows the SM count)
+    # ---- bootstrap values: the critic alone, split by head ----
+    npack, progs = describe(4096, 1)
+    assert npack == 8 and list(map(widths, progs)) == [[128, 128, 128, 1]] * 2
+    # ---- update(): forward + loss, backward ----
+    npack, (actor, critic) = describe(40960, 2)
+    assert npack == 30 and widths(actor) == [64, 20, 128, 128, 128, 12, 128, 128, 6] and widths(critic) == [128, 128, 128, 1, 128, 128, 1]
+    assert [(i, o["fin"], o["fin_c"]) for i, o in enumerate(actor[1]) if o["fin"]] == [(1, FIN_REG, 0), (5, FIN_PPO, 0), (8, FIN_PPO, 1)]
+    assert [(i, o["fin"], o["fin_c"]) for i, o in enumerate(critic[1]) if o["fin"]] == [(3, FIN_VALUE, 0), (6, FIN_VALUE, 1)]
+    assert all(o["y_img"] == (o["N"] == 128) for o in actor[1] + critic[1] if o["y"])          # 128-wide activations are kept as tile images
+    _, (actor_b, critic_b) = describe(40960, 3)
+    assert widths(actor_b) == [128] * 6 + [20, 64] and widths(critic_b) == [128] * 6
+    assert describe(40960, 2, precision="fp32") == -2 and describe(0, 0) == -1
+
+
 def test_checkpoint_round_trip_keeps_reference_names_and_shapes():
     """OPR:276-290: model_state_dict / optimizer_state_dict.  Names and order are the reference ActorCritic's (pinned by the golden file)."""
     g = np.load(os.path.join(G, "ppo.npz"))
