@@ -158,7 +158,10 @@ class FusedPPO:
             x = torch.as_tensor(x, dtype=torch.float, device=self.device)
             if x.dim() > 1 and x.shape[0] != 1:
                 raise L.DwbcError("arm coefficients must broadcast to [n_arm] (per-env coefficients are not supported)")
-            rows.append(torch.broadcast_to(x.reshape(-1) if x.dim() else x, (n_arm,)))
+            x = x.reshape(-1) if x.dim() else x
+            if x.dim() and x.numel() not in (1, n_arm):
+                raise L.DwbcError(f"arm coefficient with {x.numel()} entries does not broadcast to the {n_arm} arm joints (PPO:318-323)")
+            rows.append(torch.broadcast_to(x, (n_arm,)))
         self._arm_coefs = torch.stack(rows).contiguous()
 
     def get_torque_supervision_weight(self):

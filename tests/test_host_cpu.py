@@ -57,6 +57,11 @@ def test_torque_supervision_host_side():
     assert abs(hp.torque_supervision_weight - 0.06) < 1e-7 and hp.arm_coefs == alg._arm_coefs.data_ptr()
     with pytest.raises(L.DwbcError):
         alg.set_arm_default_coeffs(torch.zeros(4, 6), torch.zeros(6), torch.zeros(6))      # per-env coefficients
+    with pytest.raises(L.DwbcError):
+        alg.set_arm_default_coeffs(torch.zeros(6), torch.zeros(6), torch.zeros(1, 20))     # OPR:91 hands `default_dof_pos[-7:-2]` of a [1, 20] tensor
+    alg.set_arm_default_coeffs(5.0, torch.tensor(0.5), torch.zeros(6))                      # scalars broadcast
+    assert alg._arm_coefs[0].tolist() == [5.0] * 6
+    alg.set_arm_default_coeffs(torch.arange(6.0) + 5, torch.full((6,), 0.5), torch.zeros(1, 6))
     alg.init_storage(4, 3, [860], [None], [18])
     s = alg.storage
     assert s.target_arm_torques.shape == s.current_arm_dof_pos.shape == s.current_arm_dof_vel.shape == (3, 4, 6)
