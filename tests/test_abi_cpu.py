@@ -41,6 +41,26 @@ def test_debug_header_symbols_are_exported(lib):
     assert exported == sorted(L.EXPORTS + declared), set(exported) ^ set(L.EXPORTS + declared)
 
 
+def test_kernel_resource_budgets(lib):
+    """Occupancy contracts the kernels are designed around, read from the shipped cubins (`cuobjdump -res-usage`, no GPU): K1 must fit two
+    CTAs per SM (<= 128 registers at 256 threads), the chain kernel's 288 threads must stay below the 224-register cap with a small stack (a
+    change that made ptxas clone its whole item loop doubled the spills and the code size without any error), the grouped weight gradient
+    runs 21 warps per CTA (<= 96 registers)."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-res-usage", L.LIB_PATH], capture_output=True, text=True).stdout
+    use = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)", out):
+        use[m.group(1)] = tuple(int(x) for x in m.groups()[1:])
+    find = lambda key: [v for k, v in use.items() if key in k]  # noqa: E731
+    (k1,), (chain,), wg = find("env_step_v2_kernel"), find("chain2_kernel"), find("wgrad_group_kernel")
+    assert k1[0] <= 128, k1
+    assert chain[0] <= 224 and chain[1] <= 512, chain
+    assert len(wg) == 2 and all(w[0] <= 96 for w in wg), wg
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", [k for k in use if "chain2_kernel" in k][0], L.LIB_PATH], capture_output=True, text=True).stdout
+    n_instr = len(re.findall(r"^\s+/\*[0-9a-f]{4,5}\*/", sass, re.M))
+    assert 8000 < n_instr < 22000, n_instr          # 15.4 k today; 29 k when the item loop was cloned
+
+
 def test_struct_mirrors_match_c_layout(lib):
     sizes = (ctypes.c_int64 * 6)()
     lib.dwbc_struct_sizes(ctypes.byref(sizes))
